@@ -1,0 +1,180 @@
+"""GPU parity: the fused CUDA tick (through the C ABI) vs the CPU oracle, bit for bit.
+
+The numerics contract makes poses, ranges, rewards and flags exactly
+reproducible, so every comparison here is np.array_equal on the raw bits — tighter than
+the north-star's 1e-4 fp32 tolerance (collision flags bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_outputs_equal, assert_state_equal, make_pair, random_actions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('scenario,worlds', [('stage1', 5), ('stage2', 3)])
+def test_reset_and_observe_match_oracle(built, scenario, worlds):
+    sc, env, orc = make_pair(scenario, num_worlds=worlds)
+    orc.reset_world()
+    assert_state_equal(env, orc, 'after reset_world')
+    env.reset_pose()
+    orc.reset_pose()
+    assert_state_equal(env, orc, 'after reset_pose')
+    assert_outputs_equal(env, orc, 'first observation')
+
+
+@pytest.mark.parametrize('scenario,worlds,beams', [('stage1', 5, 512), ('stage2', 2, 512), ('stage1', 2, 180)])
+def test_rollout_bit_exact(built, scenario, worlds, beams):
+    sc, env, orc = make_pair(scenario, num_worlds=worlds, beams=beams, auto_reset=True, seed=7)
+    env.reset_pose()
+    orc.reset_world()
+    orc.reset_pose()
+    rng = np.random.default_rng(1)
+    seen = np.zeros(4, int)
+    for t in range(260):
+        a = random_actions(rng, orc.N, wide=True)
+        if t % 37 == 5:
+            a[::7] = 0.0          # exact-zero command: move (and stall update) skipped
+        if t == 11:
+            a[3] = [np.nan, np.inf]
+        env.control_vel(torch.from_numpy(a).cuda())
+        orc.step(a)
+        assert_state_equal(env, orc, f'tick {t}')
+        assert_outputs_equal(env, orc, f'tick {t}')
+        torch.cuda.synchronize()
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), orc.reward.view(np.uint32)), f'reward tick {t}'
+        assert np.array_equal(env.flags.cpu().numpy(), orc.flags), f'flags tick {t}'
+        done = orc.flags[:, 0] != 0
+        assert np.array_equal(env.eplog.cpu().numpy()[done], orc.eplog[done]), f'eplog tick {t}'
+        for k in range(4):
+            seen[k] += int((orc.flags[:, 2] == k).sum())
+    # the rollout must actually have exercised crashes, time-outs (stage1: 150) and re-spawns
+    assert seen[2] > 0 and seen[3] > 0, seen
+
+
+def test_manual_reset_and_live_mask(built):
+    """Stage-2 style group-synchronous episodes: no auto reset, finished agents idle on their
+    last command with live=0 (ppo_stage2.py:72-84), then a masked reset_pose."""
+    sc, env, orc = make_pair('stage2', num_worlds=2, auto_reset=False, seed=3)
+    env.reset_pose()
+    orc.reset_world()
+    orc.reset_pose()
+    rng = np.random.default_rng(5)
+    live = np.ones(orc.N, np.uint8)
+    for t in range(120):
+        a = random_actions(rng, orc.N)
+        env.control_vel(torch.from_numpy(a).cuda(), live=torch.from_numpy(live).cuda())
+        orc.step(a, live=live)
+        assert_state_equal(env, orc, f'tick {t}')
+        assert_outputs_equal(env, orc, f'tick {t}')
+        assert np.array_equal(env.flags.cpu().numpy(), orc.flags)
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), orc.reward.view(np.uint32))
+        live[orc.flags[:, 0] != 0] = 0
+        if t == 80:
+            mask = (live == 0).astype(np.uint8)
+            assert mask.sum() > 0
+            env.reset_pose(torch.from_numpy(mask).cuda())
+            orc.reset_pose(mask)
+            live[:] = 1
+            assert_state_equal(env, orc, 'masked reset')
+            assert_outputs_equal(env, orc, 'masked reset')
+
+
+def test_ctas_per_world_invariance(built):
+    """The launch shape (CTAs cooperating on one world) must not change any result."""
+    outs = []
+    for s in (1, 3, 8):
+        sc, env, orc = make_pair('stage1', num_worlds=4, seed=11, ctas_per_world=s)
+        env.reset_pose()
+        rng = np.random.default_rng(2)
+        for t in range(40):
+            env.control_vel(torch.from_numpy(random_actions(rng, orc.N)).cuda())
+        torch.cuda.synchronize()
+        outs.append((env.obs.cpu().numpy().copy(), env.state['pose'].cpu().numpy().copy(),
+                     env.reward.cpu().numpy().copy(), env.flags.cpu().numpy().copy()))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('scenario', ['stage1', 'stage2'])
+def test_standalone_raycast_matches_oracle(built, scenario):
+    sc, env, orc = make_pair(scenario, num_worlds=6, seed=1)
+    rng = np.random.default_rng(9)
+    half = 9.0 if scenario == 'stage1' else 19.0
+    pose = np.zeros((orc.N, 4), np.float32)
+    pose[:, 0] = rng.uniform(-half, half, orc.N)
+    pose[:, 1] = rng.uniform(-half, half, orc.N)
+    pose[:, 2] = rng.uniform(-np.pi, np.pi, orc.N)
+    pose[5, :2] = [half + 50.0, 0.0]       # a robot far outside the map: every beam misses
+    for normalise in (False, True):
+        got = env.raycast(torch.from_numpy(pose).cuda(), normalise=normalise).cpu().numpy()
+        ref = orc.raycast(pose, normalise=normalise)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), np.abs(got - ref).max()
+    raw = orc.raycast(pose)
+    assert raw.min() >= 0.0 and raw.max() <= 6.0 + 1e-5
+    assert np.all(raw[5] == 6.0)
+
+
+def test_headline_size_properties(built):
+    """BASELINE headline size (171 worlds x 24 robots x 512 beams): size-independent properties.
+    (1) determinism, (2) world independence: world w of the big batch equals the same world run
+    alone with the matching global world offset, checked against the oracle for a few worlds."""
+    worlds = 171
+    sc, env, _ = make_pair('stage1', num_worlds=worlds, seed=0, gpu=True)
+    env.reset_pose()
+    rng = np.random.default_rng(4)
+    acts = [random_actions(rng, env.N) for _ in range(30)]
+    for a in acts:
+        env.control_vel(torch.from_numpy(a).cuda())
+    torch.cuda.synchronize()
+    obs_big = env.obs.cpu().numpy()
+    pose_big = env.state['pose'].cpu().numpy()
+    assert obs_big.min() >= -0.5 and obs_big.max() <= 0.5 + 1e-6
+    # same thing again -> identical
+    sc2, env2, _ = make_pair('stage1', num_worlds=worlds, seed=0)
+    env2.reset_pose()
+    for a in acts:
+        env2.control_vel(torch.from_numpy(a).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(env2.obs.cpu().numpy(), obs_big)
+    # worlds 100..102 alone on the oracle with world_offset=100
+    R = 24
+    _, _, orc = make_pair('stage1', num_worlds=3, seed=0, world_offset=100, gpu=False)
+    orc.reset_world()
+    orc.reset_pose()
+    for a in acts:
+        orc.step(a[100 * R:103 * R])
+    assert np.array_equal(orc.obs.view(np.uint32), obs_big[100 * R:103 * R].view(np.uint32))
+    assert np.array_equal(orc.pose.view(np.uint32), pose_big[100 * R:103 * R].view(np.uint32))
+
+
+def test_step_host_matches_device_path(built):
+    sc, env, orc = make_pair('stage1', num_worlds=4, seed=2)
+    env.reset_pose()
+    orc.reset_world()
+    orc.reset_pose()
+    rng = np.random.default_rng(3)
+    a_host = torch.empty(orc.N, 2).pin_memory()
+    for t in range(20):
+        a = random_actions(rng, orc.N)
+        a_host.copy_(torch.from_numpy(a))
+        h = env.step_host(a_host)
+        orc.step(a)
+        assert np.array_equal(h['obs'].numpy().view(np.uint32), orc.obs.view(np.uint32))
+        assert np.array_equal(h['reward'].numpy().view(np.uint32), orc.reward.view(np.uint32))
+        assert np.array_equal(h['flags'].numpy(), orc.flags)
+
+
+def test_errors_are_loud(built):
+    import ctypes as C
+    from rl_collision_avoidance_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.EnvConfig()
+    h = C.c_void_p()
+    assert lib.rlca_env_create(C.byref(cfg), C.byref(h)) != 0      # empty config is invalid
+    assert b'robots_per_world' in lib.rlca_last_error()
+    sc, env, _ = make_pair('stage1', num_worlds=1)
+    with pytest.raises(_lib.RlcaError):
+        env.raycast(torch.zeros(env.N, 4), normalise=False, out=None) if False else _lib.check(
+            lib.rlca_raycast(env._h, None, None, 0, None))
