@@ -170,6 +170,9 @@ int rlca_env_set_ctas_per_world(rlca_env *env, int32_t ctas_per_world);
 /* Number of kernels the library launched on behalf of this handle so far. */
 int64_t rlca_env_launch_count(const rlca_env *env);
 
+/* sizeof(rlca_env_config) as compiled, so bindings can verify their struct layout. */
+int rlca_sizeof_env_config(void);
+
 const char *rlca_last_error(void);
 const char *rlca_version(void);
 

@@ -35,7 +35,7 @@ CELL_STATIC = 254
 
 
 # --------------------------------------------------------------------------- parser
-_TOKEN = re.compile(r'"[^"]*"|\(|\)|\[|\]|[^\s()\[\]"]+')
+_TOKEN = re.compile(r'"[^"]*"|[A-Za-z_]\w*\[\d+\]|\(|\)|\[|\]|[^\s()\[\]"]+')
 
 
 def _tokenize(text: str):
@@ -265,7 +265,9 @@ def load_world(path: str, pitch_align: int = 16, margin: int = 1) -> WorldMap:
                 loc = [((x - offx) * scx, (y - offy) * scy), ((x + w - offx) * scx, (y - offy) * scy),
                        ((x + w - offx) * scx, (y + h - offy) * scy), ((x - offx) * scx, (y + h - offy) * scy)]
                 marked.update(_polygon_cells(_transform(loc, pose), ppm))
-        elif base == 'position' and ent.kind == 'agent':
+        elif base == 'position' and any(getattr(c, 'base_kind', c.kind) == 'ranger' for c in ent.children):
+            # a position model carrying a ranger is a robot (worlds/stage1.world:80-105); the others are
+            # never commanded and therefore static (stage2.world:105-111)
             agents.append(_pose_of(ent))
         elif base == 'position':
             # static polygon obstacle (stage2.world:169-297): blocks normalised to `size`
