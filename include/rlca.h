@@ -170,6 +170,90 @@ int rlca_env_set_ctas_per_world(rlca_env *env, int32_t ctas_per_world);
 /* Number of kernels the library launched on behalf of this handle so far. */
 int64_t rlca_env_launch_count(const rlca_env *env);
 
+
+/* =====================================================================================
+ * Learning half: CNNPolicy forward/backward, PPO loss, GAE, Adam.
+ * Replaces the PyTorch library calls of model/net.py:37-80 and model/ppo.py:122-194.
+ *
+ * Parameters live in ONE flat fp32 buffer of RLCA_POLICY_NPARAMS floats laid out in the
+ * order of the reference's state_dict (model/net.py:16-34):
+ *   logstd(2) | act_fea_cv1.w(32,3,5) .b(32) | act_fea_cv2.w(32,32,3) .b(32) | act_fc1.w(256,4096) .b(256)
+ *   | act_fc2.w(128,260) .b(128) | actor1.w(1,128) .b(1) | actor2.w(1,128) .b(1)
+ *   | crt_fea_cv1 ... crt_fc2 (same shapes) | critic.w(1,128) .b(1)
+ * rlca_policy_param_offset(i) returns the float offset of tensor i (0..22) in that order,
+ * and i == 23 returns the total.  Gradients and Adam moments use the same layout, so the
+ * optimizer is one fused elementwise kernel and the data-parallel all-reduce one buffer.
+ * ===================================================================================== */
+#define RLCA_POLICY_NPARAMS 2172101
+#define RLCA_POLICY_NTENSORS 23
+#define RLCA_OBS_FRAMES 3
+#define RLCA_OBS_BEAMS 512
+
+typedef struct rlca_policy rlca_policy;   /* workspace (activations kept for backward) */
+
+int64_t rlca_policy_param_offset(int32_t tensor_index);
+int64_t rlca_policy_param_size(int32_t tensor_index);     /* unpadded element count of tensor i */
+int64_t rlca_policy_launch_count(const rlca_policy *pol);
+
+/* Workspace sized for batches up to max_batch rows. */
+int rlca_policy_create(int32_t max_batch, rlca_policy **out);
+int rlca_policy_destroy(rlca_policy *pol);
+
+/* CNNPolicy.forward without sampling (model/net.py:37-70): obs (nb,3,512), gs (nb,4) =
+ * local goal x,y + speed v,w  ->  value (nb), mean (nb,2).  Activations stay in the
+ * workspace for rlca_policy_backward. */
+int rlca_policy_forward(rlca_policy *pol, const float *params_dev, const float *obs_dev, const float *gs_dev,
+                        int32_t nb, float *value_dev, float *mean_dev, void *stream);
+
+/* action ~ N(mean, exp(logstd)) with a counter-based generator (replaces torch.normal,
+ * model/net.py:53-55), logprob = log_normal_density summed over the 2 dims
+ * (model/utils.py:90-97), scaled = clip(action, [v_min,w_min], [v_max,w_max]) (model/ppo.py:75).
+ * deterministic == 1 -> action = mean (generate_action_no_sampling, model/ppo.py:84-107);
+ * deterministic == 2 -> action_dev is an INPUT and only its logprob is evaluated (evaluate_actions, model/net.py:72-80). */
+int rlca_policy_sample(const float *params_dev, const float *mean_dev, int32_t nb, uint64_t seed, uint64_t counter,
+                       int32_t deterministic, float *action_dev, float *logprob_dev, float *scaled_dev, void *stream);
+
+/* Clipped-surrogate + value + entropy loss of one minibatch and its gradient w.r.t. the
+ * network outputs (model/ppo.py:172-185): loss = -mean(min(r*A, clamp(r,1-c,1+c)*A))
+ * + value_coef*MSE(V,target) - coeff_entropy*entropy.  losses_dev[0..2] = policy_loss,
+ * value_loss, entropy (the three numbers logged to ppo.log, model/ppo.py:189-192).  The output
+ * gradients stay in the workspace for rlca_policy_backward. */
+int rlca_ppo_loss_fwd_bwd(rlca_policy *pol, const float *params_dev, const float *value_dev, const float *mean_dev,
+                          const float *action_dev, const float *old_logprob_dev, const float *adv_dev,
+                          const float *target_dev, int32_t nb, float clip_value, float coeff_entropy,
+                          float value_coef, float *losses_dev, void *stream);
+
+/* Backward of the whole network for the batch of the last rlca_policy_forward: writes the
+ * flat gradient buffer (RLCA_POLICY_NPARAMS floats; overwritten, not accumulated). */
+int rlca_policy_backward(rlca_policy *pol, const float *params_dev, const float *obs_dev, const float *gs_dev,
+                         int32_t nb, float *grads_dev, void *stream);
+
+/* torch.optim.Adam step (ppo_stage1.py:179: lr 5e-5, betas (0.9,0.999), eps 1e-8, no decay),
+ * bias-corrected, step counted from 1, over n contiguous floats. */
+int rlca_adam_step(float *params_dev, const float *grads_dev, float *exp_avg_dev, float *exp_avg_sq_dev, int64_t n,
+                   float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void *stream);
+
+/* generate_train_data (model/ppo.py:122-139): GAE(gamma, lam) over (T,N) time-major arrays,
+ * reverse recurrence evaluated in float64 like the reference's numpy; fp32 outputs. */
+int rlca_gae(const float *rewards_dev, const float *values_dev, const float *last_value_dev, const uint8_t *dones_dev,
+             int32_t num_step, int32_t num_env, float gamma, float lam, float *targets_dev, float *advs_dev,
+             void *stream);
+
+/* advs = (advs - mean)/std over the whole rollout (model/ppo.py:148: numpy mean/std, ddof 0, float64, no epsilon)
+ * in two phases so that a data-parallel caller can all-reduce moments_dev (3 doubles: sum, sum of squares,
+ * count) in between. */
+int rlca_adv_moments(const float *x_dev, int64_t n, double *moments_dev, void *stream);
+int rlca_adv_apply(const float *x_dev, int64_t n, const double *moments_dev, float *out_dev, void *stream);
+
+/* dst[i,:] = src[idx[i],:] (rows of row_floats floats): random minibatch assembly (model/ppo.py:158-169). */
+int rlca_gather_rows(const float *src_dev, const int64_t *idx_dev, int32_t row_floats, int32_t nrows, float *dst_dev,
+                     void *stream);
+
+/* Observation stack push (the deque of ppo_stage1.py:60,87-89): stack_out[:,0:2] = stack_in[:,1:3],
+ * stack_out[:,2] = obs; agents whose flags say was_reset get three copies of obs. */
+int rlca_obs_stack_push(const float *stack_in_dev, const float *obs_dev, const uint8_t *flags_dev, int32_t n,
+                        int32_t beams, float *stack_out_dev, void *stream);
+
 /* sizeof(rlca_env_config) as compiled, so bindings can verify their struct layout. */
 int rlca_sizeof_env_config(void);
 

@@ -67,6 +67,23 @@ SYMBOLS = {
     'rlca_env_set_ctas_per_world': (C.c_int, [_P, C.c_int32]),
     'rlca_env_launch_count': (C.c_int64, [_P]),
     'rlca_sizeof_env_config': (C.c_int, []),
+    'rlca_policy_param_offset': (C.c_int64, [C.c_int32]),
+    'rlca_policy_param_size': (C.c_int64, [C.c_int32]),
+    'rlca_policy_launch_count': (C.c_int64, [_P]),
+    'rlca_policy_create': (C.c_int, [C.c_int32, C.POINTER(_P)]),
+    'rlca_policy_destroy': (C.c_int, [_P]),
+    'rlca_policy_forward': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    'rlca_policy_sample': (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, _P, _P, _P, _P]),
+    'rlca_ppo_loss_fwd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                        _P, _P]),
+    'rlca_policy_backward': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
+    'rlca_adam_step': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                 C.c_float, _P]),
+    'rlca_gae': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P]),
+    'rlca_adv_moments': (C.c_int, [_P, C.c_int64, _P, _P]),
+    'rlca_adv_apply': (C.c_int, [_P, C.c_int64, _P, _P, _P]),
+    'rlca_gather_rows': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    'rlca_obs_stack_push': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     'rlca_last_error': (C.c_char_p, []),
     'rlca_version': (C.c_char_p, []),
 }

@@ -1,0 +1,1037 @@
+// rlca_policy.cu — CNNPolicy forward/backward, PPO loss, GAE, Adam for sm_100a (C ABI in include/rlca.h).
+//
+// Round-1 layout of the learner: every op is a hand-written CUDA kernel (no cuDNN/cuBLAS/ATen):
+//   conv tower   fused conv1+ReLU+conv2+ReLU per (sample, tower), activations in shared memory
+//   fc1 / fc2    tiled fp32 GEMM with fused bias / ReLU / mask epilogues (fc1 has a tcgen05 path in
+//                rlca_gemm_tc.cu when enabled)
+//   heads, sampling, PPO loss (+ its gradient), GAE (float64 recurrence), Adam: fused elementwise/reduction kernels
+// Parameters, gradients and Adam moments are flat fp32 buffers in state_dict order (tensor starts
+// padded to 32 floats so every matrix is 128-byte aligned).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+
+#include "../../include/rlca.h"
+#include "rlca_common.cuh"
+
+// ------------------------------------------------------------------------------------ layout
+static const int64_t kTensorSize[RLCA_POLICY_NTENSORS] = {
+    2, 480, 32, 3072, 32, 1048576, 256, 33280, 128, 128, 1, 128, 1,
+    480, 32, 3072, 32, 1048576, 256, 33280, 128, 128, 1};
+
+static int64_t tensor_offset(int i)
+{
+    int64_t off = 0;
+    for (int k = 0; k < i && k < RLCA_POLICY_NTENSORS; ++k) off += (kTensorSize[k] + 31) / 32 * 32;
+    return off;
+}
+
+extern "C" int64_t rlca_policy_param_offset(int32_t i)
+{
+    if (i < 0) return -1;
+    if (i >= RLCA_POLICY_NTENSORS) return tensor_offset(RLCA_POLICY_NTENSORS);
+    return tensor_offset(i);
+}
+extern "C" int64_t rlca_policy_param_size(int32_t i)
+{
+    return (i >= 0 && i < RLCA_POLICY_NTENSORS) ? kTensorSize[i] : -1;
+}
+
+enum { T_LOGSTD = 0, T_CV1W = 1, T_CV1B, T_CV2W, T_CV2B, T_FC1W, T_FC1B, T_FC2W, T_FC2B, T_A1W, T_A1B, T_A2W, T_A2B,
+       T_CRT0 = 13, T_CRITW = 21, T_CRITB = 22 };
+
+struct TowerPtrs {
+    const float *cv1w, *cv1b, *cv2w, *cv2b, *fc1w, *fc1b, *fc2w, *fc2b;
+};
+struct TowerGrads {
+    float *cv1w, *cv1b, *cv2w, *cv2b, *fc1w, *fc1b, *fc2w, *fc2b;
+};
+
+static TowerPtrs tower_ptrs(const float *p, int tower)
+{
+    const int b = tower == 0 ? T_CV1W : T_CRT0;
+    TowerPtrs t;
+    t.cv1w = p + tensor_offset(b + 0); t.cv1b = p + tensor_offset(b + 1);
+    t.cv2w = p + tensor_offset(b + 2); t.cv2b = p + tensor_offset(b + 3);
+    t.fc1w = p + tensor_offset(b + 4); t.fc1b = p + tensor_offset(b + 5);
+    t.fc2w = p + tensor_offset(b + 6); t.fc2b = p + tensor_offset(b + 7);
+    return t;
+}
+static TowerGrads tower_grads(float *p, int tower)
+{
+    const int b = tower == 0 ? T_CV1W : T_CRT0;
+    TowerGrads t;
+    t.cv1w = p + tensor_offset(b + 0); t.cv1b = p + tensor_offset(b + 1);
+    t.cv2w = p + tensor_offset(b + 2); t.cv2b = p + tensor_offset(b + 3);
+    t.fc1w = p + tensor_offset(b + 4); t.fc1b = p + tensor_offset(b + 5);
+    t.fc2w = p + tensor_offset(b + 6); t.fc2b = p + tensor_offset(b + 7);
+    return t;
+}
+
+#define FEAT 4096
+#define XLD 260          // fc2 input: 256 fc1 outputs + goal(2) + speed(2)
+#define CONV_PART 3616   // per-(sample,tower) conv gradient partials: cv2w 3072 | cv2b 32 | cv1w 480 | cv1b 32
+
+struct rlca_policy {
+    int max_batch;
+    float *F;        // [2][B][4096] relu(conv2) features, flatten order c*128+p (model/net.py:44)
+    float *X;        // [2][B][260]  relu(fc1) | goal | speed
+    float *H2;       // [2][B][128]  relu(fc2)
+    float *dOut;     // [B][4]  dL/dv, dL/dz1, dL/dz2, unused
+    float *dZ2;      // [2][B][128]
+    float *dX;       // [2][B][260]  (masked in place -> dZ1 in the first 256 columns)
+    float *dF;       // [2][B][4096]
+    float *part;     // [2][B][CONV_PART]
+    float *headpart; // [chunks][3][128 + 4]
+    float *red;      // small reduction scratch (64 floats)
+    int64_t launches;
+};
+
+// ------------------------------------------------------------------------------------ conv tower forward
+// One CTA per sample; threads 0..127 run the actor tower, 128..255 the critic tower.
+// conv1: Conv1d(3,32,k5,s2,p1) 512 -> 255 ; conv2: Conv1d(32,32,k3,s2,p1) 255 -> 128 (model/net.py:21-22,42-43).
+// h1 is kept in shared memory split into even/odd positions so conv2's stride-2 reads are conflict free:
+// stored index s = q+1 (q = -1..255, zeros at both ends); even s -> h1e[s/2], odd s -> h1o[s/2].
+struct ConvSmem {
+    float xs[3][520];            // xs[c][i+1] = x[c][i], zero padded
+    float w1[2][15][32];         // [tower][ci*5+k][co]
+    float b1[2][32];
+    float w2[2][96][32];         // [tower][ci*3+k][co]
+    float b2[2][32];
+    float h1e[2][32][132];
+    float h1o[2][32][132];
+};
+
+__device__ __forceinline__ void conv_load_common(ConvSmem &sm, const float *__restrict__ obs_n, const TowerPtrs &ta,
+                                                 const TowerPtrs &tc, int tid, int nthreads)
+{
+    for (int i = tid; i < 3 * 520; i += nthreads) {
+        int c = i / 520, j = i - c * 520;
+        sm.xs[c][j] = (j >= 1 && j <= 512) ? obs_n[c * 512 + (j - 1)] : 0.0f;
+    }
+    for (int i = tid; i < 2 * 480; i += nthreads) {
+        int t = i / 480, r = i - t * 480;
+        int co = r / 15, j = r - co * 15;                 // weight layout (co, ci, k) row-major
+        sm.w1[t][j][co] = (t == 0 ? ta.cv1w : tc.cv1w)[r];
+    }
+    for (int i = tid; i < 2 * 3072; i += nthreads) {
+        int t = i / 3072, r = i - t * 3072;
+        int co = r / 96, j = r - co * 96;
+        sm.w2[t][j][co] = (t == 0 ? ta.cv2w : tc.cv2w)[r];
+    }
+    if (tid < 64) {
+        int t = tid >> 5, c = tid & 31;
+        sm.b1[t][c] = (t == 0 ? ta.cv1b : tc.cv1b)[c];
+        sm.b2[t][c] = (t == 0 ? ta.cv2b : tc.cv2b)[c];
+    }
+    for (int i = tid; i < 2 * 32; i += nthreads) {
+        int t = i >> 5, c = i & 31;
+        sm.h1e[t][c][0] = 0.0f;        // s = 0   (q = -1)
+        sm.h1e[t][c][128] = 0.0f;      // s = 256 (q = 255)
+    }
+}
+
+// conv1 + ReLU for one tower by 128 threads (lt = 0..127): positions lt and lt+128.
+__device__ __forceinline__ void conv1_tower(ConvSmem &sm, int t, int lt)
+{
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+        const int p = lt + rep * 128;
+        if (p >= 255) break;
+        float xv[15];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) xv[ci * 5 + k] = sm.xs[ci][2 * p + k];   // input idx 2p+k-1, +1 offset
+        const int s = p + 1;
+        float *dst = (s & 1) ? &sm.h1o[t][0][s >> 1] : &sm.h1e[t][0][s >> 1];
+#pragma unroll
+        for (int cg = 0; cg < 8; ++cg) {
+            float4 acc = *reinterpret_cast<const float4 *>(&sm.b1[t][cg * 4]);
+#pragma unroll
+            for (int j = 0; j < 15; ++j) {
+                const float4 w = *reinterpret_cast<const float4 *>(&sm.w1[t][j][cg * 4]);
+                acc.x = fmaf(xv[j], w.x, acc.x); acc.y = fmaf(xv[j], w.y, acc.y);
+                acc.z = fmaf(xv[j], w.z, acc.z); acc.w = fmaf(xv[j], w.w, acc.w);
+            }
+            dst[(cg * 4 + 0) * 132] = fmaxf(acc.x, 0.0f);
+            dst[(cg * 4 + 1) * 132] = fmaxf(acc.y, 0.0f);
+            dst[(cg * 4 + 2) * 132] = fmaxf(acc.z, 0.0f);
+            dst[(cg * 4 + 3) * 132] = fmaxf(acc.w, 0.0f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__restrict__ obs, TowerPtrs ta, TowerPtrs tc,
+                                                             float *__restrict__ F, int nb)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smem_raw);
+    const int n = blockIdx.x, tid = threadIdx.x;
+    conv_load_common(sm, obs + (size_t)n * 1536, ta, tc, tid, 256);
+    __syncthreads();
+    const int t = tid >> 7, lt = tid & 127;
+    conv1_tower(sm, t, lt);
+    __syncthreads();
+    // conv2: thread = 4 positions (pg + 32 i) x 8 channels (cg*8 ..)
+    const int pg = lt & 31, cg = lt >> 5;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = sm.b2[t][cg * 8 + c];
+#pragma unroll 2
+    for (int ci = 0; ci < 32; ++ci) {
+        float a0[4], a1[4], a2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = pg + 32 * i;
+            a0[i] = sm.h1e[t][ci][p];        // k = 0: s = 2p
+            a1[i] = sm.h1o[t][ci][p];        // k = 1: s = 2p+1
+            a2[i] = sm.h1e[t][ci][p + 1];    // k = 2: s = 2p+2
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 wa = *reinterpret_cast<const float4 *>(&sm.w2[t][ci * 3 + k][cg * 8]);
+            const float4 wb = *reinterpret_cast<const float4 *>(&sm.w2[t][ci * 3 + k][cg * 8 + 4]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float a = k == 0 ? a0[i] : (k == 1 ? a1[i] : a2[i]);
+                acc[i][0] = fmaf(a, wa.x, acc[i][0]); acc[i][1] = fmaf(a, wa.y, acc[i][1]);
+                acc[i][2] = fmaf(a, wa.z, acc[i][2]); acc[i][3] = fmaf(a, wa.w, acc[i][3]);
+                acc[i][4] = fmaf(a, wb.x, acc[i][4]); acc[i][5] = fmaf(a, wb.y, acc[i][5]);
+                acc[i][6] = fmaf(a, wb.z, acc[i][6]); acc[i][7] = fmaf(a, wb.w, acc[i][7]);
+            }
+        }
+    }
+    float *out = F + ((size_t)t * nb + n) * FEAT;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) out[(cg * 8 + c) * 128 + pg + 32 * i] = fmaxf(acc[i][c], 0.0f);
+}
+
+// ------------------------------------------------------------------------------------ conv tower backward
+// One CTA per (sample, tower), 256 threads.  dF (already masked by relu(conv2)) is d(conv2 pre-activation).
+struct ConvBwdSmem {
+    float xs[3][520];
+    float w1[15][32];
+    float b1[32];
+    float w2[96][32];            // [ci*3+k][co]
+    float h1e[32][132], h1o[32][132];
+    float g2[32][128];           // d conv2 pre-activation [co][p]
+    float g1e[32][132], g1o[32][132];   // d conv1 pre-activation, same even/odd layout as h1 (s = q+1)
+};
+
+__global__ void __launch_bounds__(256) conv_tower_bwd_kernel(const float *__restrict__ obs, TowerPtrs ta, TowerPtrs tc,
+                                                             const float *__restrict__ dF, float *__restrict__ part,
+                                                             int nb)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    ConvBwdSmem &sm = *reinterpret_cast<ConvBwdSmem *>(smem_raw);
+    const int n = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+    const TowerPtrs &tp = t == 0 ? ta : tc;
+    const float *obs_n = obs + (size_t)n * 1536;
+    for (int i = tid; i < 3 * 520; i += 256) {
+        int c = i / 520, j = i - c * 520;
+        sm.xs[c][j] = (j >= 1 && j <= 512) ? obs_n[c * 512 + (j - 1)] : 0.0f;
+    }
+    for (int r = tid; r < 480; r += 256) { int co = r / 15, j = r - co * 15; sm.w1[j][co] = tp.cv1w[r]; }
+    for (int r = tid; r < 3072; r += 256) { int co = r / 96, j = r - co * 96; sm.w2[j][co] = tp.cv2w[r]; }
+    if (tid < 32) {
+        sm.b1[tid] = tp.cv1b[tid];
+        sm.h1e[tid][0] = 0.f; sm.h1e[tid][128] = 0.f;
+        sm.g1e[tid][0] = 0.f; sm.g1e[tid][128] = 0.f;
+    }
+    const float *dF_n = dF + ((size_t)t * nb + n) * FEAT;
+    for (int i = tid; i < 4096; i += 256) sm.g2[i >> 7][i & 127] = dF_n[i];
+    __syncthreads();
+    // recompute h1 = relu(conv1(x))  (256 threads: position tid, tid < 255)
+    if (tid < 255) {
+        const int p = tid;
+        float xv[15];
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) xv[ci * 5 + k] = sm.xs[ci][2 * p + k];
+        const int s = p + 1;
+        float *dst = (s & 1) ? &sm.h1o[0][s >> 1] : &sm.h1e[0][s >> 1];
+#pragma unroll
+        for (int cg = 0; cg < 8; ++cg) {
+            float4 acc = *reinterpret_cast<const float4 *>(&sm.b1[cg * 4]);
+#pragma unroll
+            for (int j = 0; j < 15; ++j) {
+                const float4 w = *reinterpret_cast<const float4 *>(&sm.w1[j][cg * 4]);
+                acc.x = fmaf(xv[j], w.x, acc.x); acc.y = fmaf(xv[j], w.y, acc.y);
+                acc.z = fmaf(xv[j], w.z, acc.z); acc.w = fmaf(xv[j], w.w, acc.w);
+            }
+            dst[(cg * 4 + 0) * 132] = fmaxf(acc.x, 0.0f);
+            dst[(cg * 4 + 1) * 132] = fmaxf(acc.y, 0.0f);
+            dst[(cg * 4 + 2) * 132] = fmaxf(acc.z, 0.0f);
+            dst[(cg * 4 + 3) * 132] = fmaxf(acc.w, 0.0f);
+        }
+    }
+    __syncthreads();
+    float *out = part + ((size_t)t * nb + n) * CONV_PART;
+    // (a) dW2[co][ci][k] = sum_p g2[co][p] * h1[ci][2p+k-1]; thread: co = tid>>3, ci = (tid&7)*4 .. +3
+    {
+        const int co = tid >> 3, ci0 = (tid & 7) * 4;
+        float acc[4][3];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = 0.0f;
+        for (int p = 0; p < 128; p += 4) {
+            const float4 g = *reinterpret_cast<const float4 *>(&sm.g2[co][p]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float4 e = *reinterpret_cast<const float4 *>(&sm.h1e[ci0 + a][p]);
+                const float e4 = sm.h1e[ci0 + a][p + 4];
+                const float4 o = *reinterpret_cast<const float4 *>(&sm.h1o[ci0 + a][p]);
+                acc[a][0] = fmaf(g.x, e.x, fmaf(g.y, e.y, fmaf(g.z, e.z, fmaf(g.w, e.w, acc[a][0]))));
+                acc[a][1] = fmaf(g.x, o.x, fmaf(g.y, o.y, fmaf(g.z, o.z, fmaf(g.w, o.w, acc[a][1]))));
+                acc[a][2] = fmaf(g.x, e.y, fmaf(g.y, e.z, fmaf(g.z, e.w, fmaf(g.w, e4, acc[a][2]))));
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) out[co * 96 + (ci0 + a) * 3 + k] = acc[a][k];
+    }
+    // (b) db2[co] = sum_p g2[co][p]  (one warp-row each: 32 threads x 4 values, shuffle reduce)
+    {
+        const int w = tid >> 5, lane = tid & 31;
+        for (int co = w; co < 32; co += 8) {
+            const float4 g = *reinterpret_cast<const float4 *>(&sm.g2[co][lane * 4]);
+            float sacc = (g.x + g.y) + (g.z + g.w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (lane == 0) out[3072 + co] = sacc;
+        }
+    }
+    // (c) dh1[ci][q] = sum_co sum_k g2[co][p] w2[co][ci][k], q = 2p+k-1, masked by h1 > 0.
+    //     work item = (m = 0..127, ci group of 4): q = 2m (k=1,p=m) and q = 2m+1 (k=0,p=m+1 ; k=2,p=m)
+    for (int wi = tid; wi < 128 * 8; wi += 256) {
+        const int m = wi & 127, ci0 = (wi >> 7) * 4;
+        float ev[4] = {0.f, 0.f, 0.f, 0.f}, od[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int co = 0; co < 32; ++co) {
+            const float gm = sm.g2[co][m];
+            const float gm1 = m < 127 ? sm.g2[co][m + 1] : 0.0f;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float w0 = sm.w2[(ci0 + a) * 3 + 0][co], w1v = sm.w2[(ci0 + a) * 3 + 1][co],
+                            w2v = sm.w2[(ci0 + a) * 3 + 2][co];
+                ev[a] = fmaf(gm, w1v, ev[a]);
+                od[a] = fmaf(gm1, w0, fmaf(gm, w2v, od[a]));
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            // q = 2m -> s = 2m+1 (odd, index m) ; q = 2m+1 -> s = 2m+2 (even, index m+1); q = 255 does not exist
+            sm.g1o[ci0 + a][m] = sm.h1o[ci0 + a][m] > 0.0f ? ev[a] : 0.0f;
+            if (m < 127) sm.g1e[ci0 + a][m + 1] = sm.h1e[ci0 + a][m + 1] > 0.0f ? od[a] : 0.0f;
+        }
+    }
+    __syncthreads();
+    // (d) dW1[co][ci][k] = sum_p g1[co][p] * x[ci][2p+k-1] ; db1[co] = sum_p g1[co][p]   (p = 0..254, s = p+1)
+    for (int o = tid; o < 480 + 32; o += 256) {
+        float acc = 0.0f;
+        if (o < 480) {
+            const int co = o / 15, j = o - co * 15, ci = j / 5, k = j - ci * 5;
+            for (int p = 0; p < 255; ++p) {
+                const int s = p + 1;
+                const float g = (s & 1) ? sm.g1o[co][s >> 1] : sm.g1e[co][s >> 1];
+                acc = fmaf(g, sm.xs[ci][2 * p + k], acc);
+            }
+            out[3104 + o] = acc;
+        } else {
+            const int co = o - 480;
+            for (int p = 0; p < 255; ++p) {
+                const int s = p + 1;
+                acc += (s & 1) ? sm.g1o[co][s >> 1] : sm.g1e[co][s >> 1];
+            }
+            out[3104 + 480 + co] = acc;
+        }
+    }
+}
+
+// sum the per-sample conv partials over the batch: grid (ceil(CONV_PART/256), 2)
+__global__ void conv_part_reduce_kernel(const float *__restrict__ part, int nb, TowerGrads ga, TowerGrads gc)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (j >= CONV_PART) return;
+    const float *src = part + (size_t)t * nb * CONV_PART + j;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int n = 0;
+    for (; n + 3 < nb; n += 4) {
+        a0 += src[(size_t)(n + 0) * CONV_PART]; a1 += src[(size_t)(n + 1) * CONV_PART];
+        a2 += src[(size_t)(n + 2) * CONV_PART]; a3 += src[(size_t)(n + 3) * CONV_PART];
+    }
+    for (; n < nb; ++n) a0 += src[(size_t)n * CONV_PART];
+    const float v = (a0 + a1) + (a2 + a3);
+    const TowerGrads &g = t == 0 ? ga : gc;
+    if (j < 3072) g.cv2w[j] = v;
+    else if (j < 3104) g.cv2b[j - 3072] = v;
+    else if (j < 3584) g.cv1w[j - 3104] = v;
+    else g.cv1b[j - 3584] = v;
+}
+
+// ------------------------------------------------------------------------------------ fp32 GEMM
+// C[M,N] = epilogue( sum_k A(m,k) B(k,n) ).  A(m,k) = TA ? A[k*lda+m] : A[m*lda+k];
+// B(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n].  Epilogue: + bias[n], ReLU, multiply by (mask[m*ldc+n] > 0).
+// 64x64x16 tiles, 256 threads, 4x4 micro-tile.  blockIdx.z selects one of up to two independent problems
+// (the actor and the critic tower) so both towers share a launch.
+struct GemmProblem {
+    const float *A, *B, *bias, *mask;
+    float *C;
+};
+struct GemmArgs {
+    GemmProblem pr[2];
+    int M, N, K, lda, ldb, ldc;
+    int relu;
+};
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
+{
+    __shared__ __align__(16) float As[16][64 + 4];
+    __shared__ __align__(16) float Bs[16][64 + 4];
+    const GemmProblem pr = blockIdx.z ? g.pr[1] : g.pr[0];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int k0 = 0; k0 < g.K; k0 += 16) {
+        // ---- A tile -> As[k][m]
+        if (!TA) {
+            const int m = tid >> 2, kq = (tid & 3) * 4;            // 64 rows x 4 float4 along k
+            const int gm = m0 + m, gk = k0 + kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gm < g.M) {
+                const float *src = pr.A + (size_t)gm * g.lda + gk;
+                if (gk + 3 < g.K) v = *reinterpret_cast<const float4 *>(src);
+                else {
+                    if (gk + 0 < g.K) v.x = src[0];
+                    if (gk + 1 < g.K) v.y = src[1];
+                    if (gk + 2 < g.K) v.z = src[2];
+                }
+            }
+            As[kq + 0][m] = v.x; As[kq + 1][m] = v.y; As[kq + 2][m] = v.z; As[kq + 3][m] = v.w;
+        } else {
+            const int k = tid >> 4, mq = (tid & 15) * 4;           // 16 k x 16 float4 along m
+            const int gk = k0 + k, gm = m0 + mq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < g.K) {
+                const float *src = pr.A + (size_t)gk * g.lda + gm;
+                if (gm + 3 < g.M) v = *reinterpret_cast<const float4 *>(src);
+                else {
+                    if (gm + 0 < g.M) v.x = src[0];
+                    if (gm + 1 < g.M) v.y = src[1];
+                    if (gm + 2 < g.M) v.z = src[2];
+                }
+            }
+            *reinterpret_cast<float4 *>(&As[k][mq]) = v;
+        }
+        // ---- B tile -> Bs[k][n]
+        if (TB) {
+            const int n = tid >> 2, kq = (tid & 3) * 4;
+            const int gn = n0 + n, gk = k0 + kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gn < g.N) {
+                const float *src = pr.B + (size_t)gn * g.ldb + gk;
+                if (gk + 3 < g.K) v = *reinterpret_cast<const float4 *>(src);
+                else {
+                    if (gk + 0 < g.K) v.x = src[0];
+                    if (gk + 1 < g.K) v.y = src[1];
+                    if (gk + 2 < g.K) v.z = src[2];
+                }
+            }
+            Bs[kq + 0][n] = v.x; Bs[kq + 1][n] = v.y; Bs[kq + 2][n] = v.z; Bs[kq + 3][n] = v.w;
+        } else {
+            const int k = tid >> 4, nq = (tid & 15) * 4;
+            const int gk = k0 + k, gn = n0 + nq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < g.K) {
+                const float *src = pr.B + (size_t)gk * g.ldb + gn;
+                if (gn + 3 < g.N) v = *reinterpret_cast<const float4 *>(src);
+                else {
+                    if (gn + 0 < g.N) v.x = src[0];
+                    if (gn + 1 < g.N) v.y = src[1];
+                    if (gn + 2 < g.N) v.z = src[2];
+                }
+            }
+            *reinterpret_cast<float4 *>(&Bs[k][nq]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= g.N) continue;
+            float v = acc[i][j];
+            if (pr.bias) v += pr.bias[gn];
+            if (g.relu) v = fmaxf(v, 0.0f);
+            if (pr.mask) v = pr.mask[(size_t)gm * g.ldc + gn] > 0.0f ? v : 0.0f;
+            pr.C[(size_t)gm * g.ldc + gn] = v;
+        }
+    }
+}
+
+template <bool TA, bool TB>
+static void launch_gemm(const GemmArgs &g, int nprob, cudaStream_t s)
+{
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, nprob);
+    gemm_kernel<TA, TB><<<grid, 256, 0, s>>>(g);
+}
+
+// ------------------------------------------------------------------------------------ small kernels
+// X[t][i][256..259] = goal xy, speed vw for both towers (torch.cat((a, goal, speed)), model/net.py:47,65)
+__global__ void fill_gs_kernel(float *__restrict__ X, const float *__restrict__ gs, int nb)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const float4 v = reinterpret_cast<const float4 *>(gs)[i];
+    reinterpret_cast<float4 *>(X + (size_t)i * XLD + 256)[0] = v;
+    reinterpret_cast<float4 *>(X + ((size_t)nb + i) * XLD + 256)[0] = v;
+}
+
+// heads: one warp per sample.  mean = (sigmoid(actor1), tanh(actor2)), v = critic (model/net.py:49-51,67)
+__global__ void heads_fwd_kernel(const float *__restrict__ H2, const float *__restrict__ a1w, const float *__restrict__ a1b,
+                                 const float *__restrict__ a2w, const float *__restrict__ a2b,
+                                 const float *__restrict__ cw, const float *__restrict__ cb, int nb,
+                                 float *__restrict__ value, float *__restrict__ mean)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= nb) return;
+    const float4 ha = reinterpret_cast<const float4 *>(H2 + (size_t)i * 128)[lane];
+    const float4 hc = reinterpret_cast<const float4 *>(H2 + ((size_t)nb + i) * 128)[lane];
+    const float4 w1 = reinterpret_cast<const float4 *>(a1w)[lane], w2 = reinterpret_cast<const float4 *>(a2w)[lane],
+                 w3 = reinterpret_cast<const float4 *>(cw)[lane];
+    float z1 = fmaf(ha.x, w1.x, fmaf(ha.y, w1.y, fmaf(ha.z, w1.z, ha.w * w1.w)));
+    float z2 = fmaf(ha.x, w2.x, fmaf(ha.y, w2.y, fmaf(ha.z, w2.z, ha.w * w2.w)));
+    float z3 = fmaf(hc.x, w3.x, fmaf(hc.y, w3.y, fmaf(hc.z, w3.z, hc.w * w3.w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+        z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+        z3 += __shfl_xor_sync(0xffffffffu, z3, o);
+    }
+    if (lane == 0) {
+        z1 += a1b[0]; z2 += a2b[0]; z3 += cb[0];
+        mean[2 * i + 0] = 1.0f / (1.0f + expf(-z1));
+        mean[2 * i + 1] = tanhf(z2);
+        value[i] = z3;
+    }
+}
+
+// dZ2[t][i][j] for both towers + per-chunk partial sums of the three head weight/bias gradients.
+// block = 128 threads (one per hidden unit j), grid = chunks of 32 samples.
+__global__ void __launch_bounds__(128) heads_bwd_kernel(const float *__restrict__ H2, const float *__restrict__ dOut,
+                                                        const float *__restrict__ a1w, const float *__restrict__ a2w,
+                                                        const float *__restrict__ cw, int nb, float *__restrict__ dZ2,
+                                                        float *__restrict__ headpart)
+{
+    const int j = threadIdx.x, c = blockIdx.x;
+    const float w1 = a1w[j], w2 = a2w[j], w3 = cw[j];
+    float g1 = 0.f, g2 = 0.f, g3 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    const int i1 = min(nb, (c + 1) * 32);
+    for (int i = c * 32; i < i1; ++i) {
+        const float4 d = reinterpret_cast<const float4 *>(dOut)[i];     // dv, dz1, dz2, _
+        const float ha = H2[(size_t)i * 128 + j], hc = H2[((size_t)nb + i) * 128 + j];
+        dZ2[(size_t)i * 128 + j] = ha > 0.0f ? fmaf(d.y, w1, d.z * w2) : 0.0f;
+        dZ2[((size_t)nb + i) * 128 + j] = hc > 0.0f ? d.x * w3 : 0.0f;
+        g1 = fmaf(d.y, ha, g1); g2 = fmaf(d.z, ha, g2); g3 = fmaf(d.x, hc, g3);
+        b1 += d.y; b2 += d.z; b3 += d.x;
+    }
+    float *o = headpart + (size_t)c * 3 * 132;
+    o[0 * 132 + j] = g1; o[1 * 132 + j] = g2; o[2 * 132 + j] = g3;
+    if (j == 0) { o[0 * 132 + 128] = b1; o[1 * 132 + 128] = b2; o[2 * 132 + 128] = b3; }
+}
+
+__global__ void heads_part_reduce_kernel(const float *__restrict__ headpart, int chunks, float *ga1w, float *ga1b,
+                                         float *ga2w, float *ga2b, float *gcw, float *gcb)
+{
+    const int j = threadIdx.x, h = blockIdx.x;     // 129 active threads, 3 blocks
+    if (j > 128) return;
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) acc += headpart[((size_t)c * 3 + h) * 132 + j];
+    float *w = h == 0 ? ga1w : (h == 1 ? ga2w : gcw), *b = h == 0 ? ga1b : (h == 1 ? ga2b : gcb);
+    if (j < 128) w[j] = acc; else b[0] = acc;
+}
+
+// out[t][j] = sum_i A[t][i*ld + j] ; grid (ceil(ncols/32), ntowers), 256 threads = 8 row groups x 32 columns
+struct ColsumArgs { const float *A[2]; float *out[2]; int rows, cols, ld; };
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumArgs a)
+{
+    __shared__ float red[8][33];
+    const int t = blockIdx.y, lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    float acc = 0.f;
+    if (j < a.cols)
+        for (int i = rg; i < a.rows; i += 8) acc += a.A[t][(size_t)i * a.ld + j];
+    red[rg][lane] = acc;
+    __syncthreads();
+    if (rg == 0 && j < a.cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += red[r][lane];
+        a.out[t][j] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------ sampling
+__device__ __forceinline__ void philox4(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+#define LOG_2PI_HALF 0.91893853320467274178f
+
+__global__ void sample_kernel(const float *__restrict__ logstd, const float *__restrict__ mean, int nb, uint64_t seed,
+                              uint64_t counter, int deterministic, float *__restrict__ action,
+                              float *__restrict__ logprob, float *__restrict__ scaled)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const float ls0 = logstd[0], ls1 = logstd[1];
+    const float m0 = mean[2 * i], m1 = mean[2 * i + 1];
+    float a0 = m0, a1 = m1;
+    if (deterministic == 2) { a0 = action[2 * i]; a1 = action[2 * i + 1]; }   // evaluate a given action
+    if (!deterministic) {
+        uint32_t c[4] = {(uint32_t)i, (uint32_t)counter, (uint32_t)(counter >> 32), 0x5A17u};
+        philox4(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        // Box-Muller on two 24-bit uniforms in (0,1]
+        const float u1 = ((float)(c[0] >> 8) + 1.0f) * 5.9604644775390625e-08f;
+        const float u2 = (float)(c[1] >> 8) * 5.9604644775390625e-08f;
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincosf(6.28318530717958647692f * u2, &sn, &cs);
+        a0 = fmaf(expf(ls0), rad * cs, m0);
+        a1 = fmaf(expf(ls1), rad * sn, m1);
+    }
+    // log_normal_density (model/utils.py:90-97)
+    const float d0 = a0 - m0, d1 = a1 - m1;
+    const float v0 = expf(2.0f * ls0), v1 = expf(2.0f * ls1);
+    const float lp = (-(d0 * d0) / (2.0f * v0) - LOG_2PI_HALF - ls0) + (-(d1 * d1) / (2.0f * v1) - LOG_2PI_HALF - ls1);
+    action[2 * i] = a0; action[2 * i + 1] = a1;
+    logprob[i] = lp;
+    if (scaled) {
+        scaled[2 * i] = fminf(fmaxf(a0, 0.0f), 1.0f);          // action_bound [[0,-1],[1,1]] (ppo_stage1.py:170)
+        scaled[2 * i + 1] = fminf(fmaxf(a1, -1.0f), 1.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------ PPO loss (+ gradient)
+// single CTA of 1024 threads; deterministic tree reductions.
+__device__ __forceinline__ float block_sum_1024(float v, float *sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = (threadIdx.x < 32) ? sh[threadIdx.x] : 0.0f;
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (threadIdx.x == 0) sh[32] = r;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+__global__ void __launch_bounds__(1024) ppo_loss_kernel(const float *__restrict__ logstd, const float *__restrict__ value,
+                                                        const float *__restrict__ mean, const float *__restrict__ action,
+                                                        const float *__restrict__ old_lp, const float *__restrict__ adv,
+                                                        const float *__restrict__ target, int nb, float clip,
+                                                        float coeff_entropy, float value_coef,
+                                                        float *__restrict__ dOut, float *__restrict__ losses,
+                                                        float *__restrict__ dlogstd)
+{
+    __shared__ float sh[34];
+    const float ls0 = logstd[0], ls1 = logstd[1];
+    const float var0 = expf(2.0f * ls0), var1 = expf(2.0f * ls1);
+    const float inv_nb = 1.0f / (float)nb;
+    float s_pl = 0.f, s_vl = 0.f, s_g0 = 0.f, s_g1 = 0.f;
+    for (int i = threadIdx.x; i < nb; i += 1024) {
+        const float m0 = mean[2 * i], m1 = mean[2 * i + 1];
+        const float d0 = action[2 * i] - m0, d1 = action[2 * i + 1] - m1;
+        const float lp = (-(d0 * d0) / (2.0f * var0) - LOG_2PI_HALF - ls0) + (-(d1 * d1) / (2.0f * var1) - LOG_2PI_HALF - ls1);
+        const float ratio = expf(lp - old_lp[i]);
+        const float A = adv[i];
+        const float s1 = ratio * A;
+        const float s2 = fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip) * A;
+        s_pl += fminf(s1, s2);
+        const float dv = value[i] - target[i];
+        s_vl += dv * dv;
+        // d(-mean(min))/d lp : gradient flows through s1 when s1 <= s2 (ties split evenly in torch and both
+        // halves reach `ratio`), else through the clamp, which is flat outside its range.
+        const float g_lp = (s1 <= s2) ? -inv_nb * A * ratio : 0.0f;
+        const float dm0 = g_lp * d0 / var0, dm1 = g_lp * d1 / var1;      // dL/dmean
+        s_g0 += g_lp * (d0 * d0 / var0 - 1.0f);
+        s_g1 += g_lp * (d1 * d1 / var1 - 1.0f);
+        reinterpret_cast<float4 *>(dOut)[i] =
+            make_float4(value_coef * 2.0f * dv * inv_nb, dm0 * m0 * (1.0f - m0), dm1 * (1.0f - m1 * m1), 0.0f);
+    }
+    const float pl = block_sum_1024(s_pl, sh), vl = block_sum_1024(s_vl, sh);
+    const float g0 = block_sum_1024(s_g0, sh), g1 = block_sum_1024(s_g1, sh);
+    if (threadIdx.x == 0) {
+        losses[0] = -pl * inv_nb;                              // policy_loss
+        losses[1] = vl * inv_nb;                               // value_loss
+        losses[2] = (0.5f + LOG_2PI_HALF + ls0) + (0.5f + LOG_2PI_HALF + ls1);   // dist_entropy (model/net.py:78-79)
+        dlogstd[0] = g0 - coeff_entropy;
+        dlogstd[1] = g1 - coeff_entropy;
+    }
+}
+
+// ------------------------------------------------------------------------------------ Adam / GAE / misc
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                            float *__restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt, float grad_scale)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * grad_scale;
+    const float mi = fmaf(b1, m[i], (1.0f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.0f - b2) * gi * gi);
+    m[i] = mi; v[i] = vi;
+    // torch.optim.Adam: denom = sqrt(v)/sqrt(bias_correction2) + eps ; p -= lr/bias_correction1 * m/denom
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+}
+
+__global__ void gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
+                           const float *__restrict__ last_value, const uint8_t *__restrict__ dones, int T, int N,
+                           double gamma, double lam, float *__restrict__ targets, float *__restrict__ advs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double gae = 0.0, vnext = (double)last_value[i];
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t k = (size_t)t * N + i;
+        const double nd = dones[k] ? 0.0 : 1.0;
+        const double v = (double)values[k];
+        const double delta = (double)rewards[k] + gamma * vnext * nd - v;
+        gae = delta + gamma * lam * nd * gae;
+        const double tgt = gae + v;
+        targets[k] = (float)tgt;
+        advs[k] = (float)(tgt - v);
+        vnext = v;
+    }
+}
+
+__global__ void obs_stack_push_kernel(const float4 *__restrict__ in, const float4 *__restrict__ obs,
+                                      const uint8_t *__restrict__ flags, int n, int b4, float4 *__restrict__ out)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n * b4) return;
+    const int a = (int)(idx / b4), j = (int)(idx - (int64_t)a * b4);
+    const float4 o = obs[idx];
+    const bool was_reset = flags != nullptr && flags[4 * a + 3] != 0;
+    const size_t base = (size_t)a * 3 * b4 + j;
+    out[base] = was_reset ? o : in[base + b4];
+    out[base + b4] = was_reset ? o : in[base + 2 * (size_t)b4];
+    out[base + 2 * (size_t)b4] = o;
+}
+
+// advs = (advs - mean) / std over the whole rollout, numpy semantics (ddof = 0, float64 moments, no epsilon):
+// model/ppo.py:148.  Single CTA; `moments` (3 doubles: sum, sum of squares, count) lets a data-parallel
+// caller all-reduce the moments between the two phases.
+__global__ void __launch_bounds__(1024) adv_moments_kernel(const float *__restrict__ x, int64_t n, double *moments)
+{
+    __shared__ double sh[2][32];
+    double s = 0.0, ss = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) { const double v = (double)x[i]; s += v; ss += v * v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = ss; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = sh[0][threadIdx.x]; ss = sh[1][threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+        if (threadIdx.x == 0) { moments[0] = s; moments[1] = ss; moments[2] = (double)n; }
+    }
+}
+
+__global__ void adv_apply_kernel(const float *__restrict__ x, int64_t n, const double *__restrict__ moments,
+                                 float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double cnt = moments[2], mean = moments[0] / cnt;
+    const double var = moments[1] / cnt - mean * mean;
+    out[i] = (float)(((double)x[i] - mean) / sqrt(var));
+}
+
+// dst[i, :] = src[idx[i], :] for rows of row_floats floats (multiple of 4): minibatch assembly (model/ppo.py:162-169)
+__global__ void gather_rows_kernel(const float4 *__restrict__ src, const int64_t *__restrict__ idx, int row4, int nrows,
+                                   float4 *__restrict__ dst)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nrows * row4) return;
+    const int r = (int)(t / row4), j = (int)(t - (int64_t)r * row4);
+    dst[t] = src[idx[r] * row4 + j];
+}
+
+__global__ void gather_scalar_kernel(const float *__restrict__ src, const int64_t *__restrict__ idx, int row, int nrows,
+                                     float *__restrict__ dst)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nrows * row) return;
+    const int r = t / row, j = t - r * row;
+    dst[t] = src[idx[r] * row + j];
+}
+
+// ------------------------------------------------------------------------------------ host API
+extern "C" int rlca_adv_moments(const float *x, int64_t n, double *moments, void *stream)
+{
+    if (!x || !moments || n < 1) return rlca_set_err(RLCA_ERR_INVALID, "bad adv_moments arguments");
+    adv_moments_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, moments);
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_adv_apply(const float *x, int64_t n, const double *moments, float *out, void *stream)
+{
+    if (!x || !moments || !out || n < 1) return rlca_set_err(RLCA_ERR_INVALID, "bad adv_apply arguments");
+    adv_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, moments, out);
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_gather_rows(const float *src, const int64_t *idx, int32_t row_floats, int32_t nrows, float *dst,
+                                void *stream)
+{
+    if (!src || !idx || !dst || row_floats < 1 || nrows < 1) return rlca_set_err(RLCA_ERR_INVALID, "bad gather arguments");
+    if ((row_floats & 3) == 0) {
+        const int row4 = row_floats / 4;
+        const int64_t total = (int64_t)nrows * row4;
+        gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4 *>(src), idx, row4, nrows, reinterpret_cast<float4 *>(dst));
+    } else {
+        const int total = nrows * row_floats;
+        gather_scalar_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, idx, row_floats, nrows, dst);
+    }
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
+{
+    if (!out || max_batch < 1) return rlca_set_err(RLCA_ERR_INVALID, "bad max_batch/out");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return rlca_set_err(RLCA_ERR_NO_DEVICE, "no CUDA device; librlca has no CPU fallback");
+    rlca_policy *p = new (std::nothrow) rlca_policy();
+    if (!p) return rlca_set_err(RLCA_ERR_INVALID, "out of host memory");
+    memset(p, 0, sizeof(*p));
+    p->max_batch = max_batch;
+    const size_t B = (size_t)max_batch;
+    const int chunks = (max_batch + 31) / 32;
+    RLCA_CUDA_TRY(cudaMalloc(&p->F, 2 * B * FEAT * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->X, 2 * B * XLD * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->H2, 2 * B * 128 * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->dOut, B * 4 * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->dZ2, 2 * B * 128 * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->dX, 2 * B * XLD * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->dF, 2 * B * FEAT * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->part, 2 * B * CONV_PART * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->headpart, (size_t)chunks * 3 * 132 * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->red, 64 * sizeof(float)));
+    RLCA_CUDA_TRY(cudaFuncSetAttribute(conv_tower_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ConvSmem)));
+    RLCA_CUDA_TRY(cudaFuncSetAttribute(conv_tower_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ConvBwdSmem)));
+    *out = p;
+    return RLCA_OK;
+}
+
+extern "C" int rlca_policy_destroy(rlca_policy *p)
+{
+    if (!p) return RLCA_OK;
+    cudaFree(p->F); cudaFree(p->X); cudaFree(p->H2); cudaFree(p->dOut); cudaFree(p->dZ2); cudaFree(p->dX);
+    cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red);
+    delete p;
+    return RLCA_OK;
+}
+
+extern "C" int64_t rlca_policy_launch_count(const rlca_policy *p) { return p ? p->launches : -1; }
+
+extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const float *obs, const float *gs, int32_t nb,
+                                   float *value, float *mean, void *stream)
+{
+    if (!pol || !params || !obs || !gs || !value || !mean) return rlca_set_err(RLCA_ERR_INVALID, "NULL argument");
+    if (nb < 1 || nb > pol->max_batch) return rlca_set_err(RLCA_ERR_INVALID, "nb exceeds the workspace max_batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    const TowerPtrs ta = tower_ptrs(params, 0), tc = tower_ptrs(params, 1);
+    conv_tower_fwd_kernel<<<nb, 256, sizeof(ConvSmem), s>>>(obs, ta, tc, pol->F, nb);
+    GemmArgs g{};
+    // fc1: X[:, :256] = relu(F W1^T + b1)
+    g.M = nb; g.N = 256; g.K = FEAT; g.lda = FEAT; g.ldb = FEAT; g.ldc = XLD; g.relu = 1;
+    g.pr[0] = GemmProblem{pol->F, ta.fc1w, ta.fc1b, nullptr, pol->X};
+    g.pr[1] = GemmProblem{pol->F + (size_t)nb * FEAT, tc.fc1w, tc.fc1b, nullptr, pol->X + (size_t)nb * XLD};
+    launch_gemm<false, true>(g, 2, s);
+    fill_gs_kernel<<<(nb + 127) / 128, 128, 0, s>>>(pol->X, gs, nb);
+    // fc2: H2 = relu(X W2^T + b2)
+    g.M = nb; g.N = 128; g.K = XLD; g.lda = XLD; g.ldb = XLD; g.ldc = 128; g.relu = 1;
+    g.pr[0] = GemmProblem{pol->X, ta.fc2w, ta.fc2b, nullptr, pol->H2};
+    g.pr[1] = GemmProblem{pol->X + (size_t)nb * XLD, tc.fc2w, tc.fc2b, nullptr, pol->H2 + (size_t)nb * 128};
+    launch_gemm<false, true>(g, 2, s);
+    heads_fwd_kernel<<<(nb * 32 + 255) / 256, 256, 0, s>>>(
+        pol->H2, params + tensor_offset(T_A1W), params + tensor_offset(T_A1B), params + tensor_offset(T_A2W),
+        params + tensor_offset(T_A2B), params + tensor_offset(T_CRITW), params + tensor_offset(T_CRITB), nb, value, mean);
+    pol->launches += 5;
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_policy_sample(const float *params, const float *mean, int32_t nb, uint64_t seed, uint64_t counter,
+                                  int32_t deterministic, float *action, float *logprob, float *scaled, void *stream)
+{
+    if (!params || !mean || !action || !logprob || nb < 1) return rlca_set_err(RLCA_ERR_INVALID, "NULL argument");
+    sample_kernel<<<(nb + 127) / 128, 128, 0, (cudaStream_t)stream>>>(params + tensor_offset(T_LOGSTD), mean, nb, seed,
+                                                                      counter, deterministic, action, logprob, scaled);
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_ppo_loss_fwd_bwd(rlca_policy *pol, const float *params, const float *value, const float *mean,
+                                     const float *action, const float *old_logprob, const float *adv,
+                                     const float *target, int32_t nb, float clip_value, float coeff_entropy,
+                                     float value_coef, float *losses, void *stream)
+{
+    if (!pol || !params || !value || !mean || !action || !old_logprob || !adv || !target || !losses)
+        return rlca_set_err(RLCA_ERR_INVALID, "NULL argument");
+    if (nb < 1 || nb > pol->max_batch) return rlca_set_err(RLCA_ERR_INVALID, "nb exceeds the workspace max_batch");
+    ppo_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params + tensor_offset(T_LOGSTD), value, mean, action,
+                                                         old_logprob, adv, target, nb, clip_value, coeff_entropy,
+                                                         value_coef, pol->dOut, losses, pol->red);
+    pol->launches += 1;
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const float *obs, const float *gs, int32_t nb,
+                                    float *grads, void *stream)
+{
+    (void)gs;
+    if (!pol || !params || !obs || !grads) return rlca_set_err(RLCA_ERR_INVALID, "NULL argument");
+    if (nb < 1 || nb > pol->max_batch) return rlca_set_err(RLCA_ERR_INVALID, "nb exceeds the workspace max_batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    const TowerPtrs ta = tower_ptrs(params, 0), tc = tower_ptrs(params, 1);
+    const TowerGrads ga = tower_grads(grads, 0), gc = tower_grads(grads, 1);
+    const size_t B = (size_t)nb;
+    // padding floats between tensors must stay zero for the optimizer / all-reduce
+    RLCA_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)tensor_offset(RLCA_POLICY_NTENSORS), s));
+    RLCA_CUDA_TRY(cudaMemcpyAsync(grads + tensor_offset(T_LOGSTD), pol->red, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    const int chunks = (nb + 31) / 32;
+    heads_bwd_kernel<<<chunks, 128, 0, s>>>(pol->H2, pol->dOut, params + tensor_offset(T_A1W),
+                                            params + tensor_offset(T_A2W), params + tensor_offset(T_CRITW), nb, pol->dZ2,
+                                            pol->headpart);
+    heads_part_reduce_kernel<<<3, 160, 0, s>>>(pol->headpart, chunks, grads + tensor_offset(T_A1W),
+                                               grads + tensor_offset(T_A1B), grads + tensor_offset(T_A2W),
+                                               grads + tensor_offset(T_A2B), grads + tensor_offset(T_CRITW),
+                                               grads + tensor_offset(T_CRITB));
+    // fc2 bias grads
+    ColsumArgs cs{};
+    cs.A[0] = pol->dZ2; cs.A[1] = pol->dZ2 + B * 128; cs.out[0] = ga.fc2b; cs.out[1] = gc.fc2b;
+    cs.rows = nb; cs.cols = 128; cs.ld = 128;
+    colsum_kernel<<<dim3(4, 2), 256, 0, s>>>(cs);
+    GemmArgs g{};
+    // dW_fc2 (128 x 260) = dZ2^T X
+    g.M = 128; g.N = XLD; g.K = nb; g.lda = 128; g.ldb = XLD; g.ldc = XLD; g.relu = 0;
+    g.pr[0] = GemmProblem{pol->dZ2, pol->X, nullptr, nullptr, ga.fc2w};
+    g.pr[1] = GemmProblem{pol->dZ2 + B * 128, pol->X + B * XLD, nullptr, nullptr, gc.fc2w};
+    launch_gemm<true, false>(g, 2, s);
+    // dX (nb x 260) = dZ2 W_fc2, masked by relu(fc1) (columns 256..259 = goal/speed carry no parameter gradient)
+    g.M = nb; g.N = 256; g.K = 128; g.lda = 128; g.ldb = XLD; g.ldc = XLD; g.relu = 0;
+    g.pr[0] = GemmProblem{pol->dZ2, ta.fc2w, nullptr, pol->X, pol->dX};
+    g.pr[1] = GemmProblem{pol->dZ2 + B * 128, tc.fc2w, nullptr, pol->X + B * XLD, pol->dX + B * XLD};
+    launch_gemm<false, false>(g, 2, s);
+    // fc1 bias grads
+    cs.A[0] = pol->dX; cs.A[1] = pol->dX + B * XLD; cs.out[0] = ga.fc1b; cs.out[1] = gc.fc1b;
+    cs.rows = nb; cs.cols = 256; cs.ld = XLD;
+    colsum_kernel<<<dim3(8, 2), 256, 0, s>>>(cs);
+    // dW_fc1 (256 x 4096) = dZ1^T F
+    g.M = 256; g.N = FEAT; g.K = nb; g.lda = XLD; g.ldb = FEAT; g.ldc = FEAT; g.relu = 0;
+    g.pr[0] = GemmProblem{pol->dX, pol->F, nullptr, nullptr, ga.fc1w};
+    g.pr[1] = GemmProblem{pol->dX + B * XLD, pol->F + B * FEAT, nullptr, nullptr, gc.fc1w};
+    launch_gemm<true, false>(g, 2, s);
+    // dF (nb x 4096) = dZ1 W_fc1, masked by relu(conv2)
+    g.M = nb; g.N = FEAT; g.K = 256; g.lda = XLD; g.ldb = FEAT; g.ldc = FEAT; g.relu = 0;
+    g.pr[0] = GemmProblem{pol->dX, ta.fc1w, nullptr, pol->F, pol->dF};
+    g.pr[1] = GemmProblem{pol->dX + B * XLD, tc.fc1w, nullptr, pol->F + B * FEAT, pol->dF + B * FEAT};
+    launch_gemm<false, false>(g, 2, s);
+    conv_tower_bwd_kernel<<<dim3(nb, 2), 256, sizeof(ConvBwdSmem), s>>>(obs, ta, tc, pol->dF, pol->part, nb);
+    conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->part, nb, ga, gc);
+    pol->launches += 10;
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                              float beta1, float beta2, float eps, int32_t step, float grad_scale, void *stream)
+{
+    if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1)
+        return rlca_set_err(RLCA_ERR_INVALID, "bad Adam arguments");
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2 = 1.0f - powf(beta2, (float)step);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr,
+                                                                            beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_gae(const float *rewards, const float *values, const float *last_value, const uint8_t *dones,
+                        int32_t T, int32_t N, float gamma, float lam, float *targets, float *advs, void *stream)
+{
+    if (!rewards || !values || !last_value || !dones || !targets || !advs || T < 1 || N < 1)
+        return rlca_set_err(RLCA_ERR_INVALID, "bad GAE arguments");
+    gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, values, last_value, dones, T, N, (double)gamma,
+                                                               (double)lam, targets, advs);
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_obs_stack_push(const float *stack_in, const float *obs, const uint8_t *flags, int32_t n,
+                                   int32_t beams, float *stack_out, void *stream)
+{
+    if (!stack_in || !obs || !stack_out || n < 1 || beams < 4 || (beams & 3))
+        return rlca_set_err(RLCA_ERR_INVALID, "bad obs_stack_push arguments");
+    const int b4 = beams / 4;
+    const int64_t total = (int64_t)n * b4;
+    obs_stack_push_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4 *>(stack_in), reinterpret_cast<const float4 *>(obs), flags, n, b4,
+        reinterpret_cast<float4 *>(stack_out));
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}

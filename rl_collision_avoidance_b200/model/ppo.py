@@ -1,0 +1,190 @@
+"""PPO functions over device tensors (mirror of /root/reference/model/ppo.py:22-259).
+
+Same names and argument order; numpy arrays become device tensors and every heavy step is a
+librlca.so kernel: GAE (float64 recurrence), advantage normalisation, minibatch gather, policy
+forward, fused clipped-surrogate/value/entropy loss + gradient, backward, fused Adam.
+`ppo.log` gets the same "policy_loss, value_loss, entropy" line per minibatch (model/ppo.py:189-192),
+written once per update from a device-side log instead of three host syncs per minibatch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+import socket
+
+import torch
+
+from .. import _lib
+from .net import CNNPolicy, _ptr
+
+logger_ppo = logging.getLogger('loggerppo')
+
+
+def setup_ppo_log(root='./log'):
+    """The reference creates ./log/<hostname>/ppo.log at import (model/ppo.py:10-19); here it is explicit."""
+    d = os.path.join(root, socket.gethostname())
+    os.makedirs(d, exist_ok=True)
+    logger_ppo.setLevel(logging.INFO)
+    if not logger_ppo.handlers:
+        h = logging.FileHandler(os.path.join(d, 'ppo.log'), mode='a')
+        h.setLevel(logging.INFO)
+        logger_ppo.addHandler(h)
+    return logger_ppo
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def transform_buffer(buff):
+    """list of (state_list, a, r, d, logprob, v) per step -> 8 stacked tensors (model/ppo.py:22-54).
+    state_list is (obs_stack (N,3,B), goal (N,2), speed (N,2))."""
+    s_batch = torch.stack([e[0][0] for e in buff])
+    goal_batch = torch.stack([e[0][1] for e in buff])
+    speed_batch = torch.stack([e[0][2] for e in buff])
+    a_batch = torch.stack([e[1] for e in buff])
+    r_batch = torch.stack([e[2] for e in buff])
+    d_batch = torch.stack([e[3] for e in buff])
+    l_batch = torch.stack([e[4] for e in buff])
+    v_batch = torch.stack([e[5] for e in buff])
+    return s_batch, goal_batch, speed_batch, a_batch, r_batch, d_batch, l_batch, v_batch
+
+
+def generate_action(env, state_list, policy, action_bound):
+    """(v, a, logprob, scaled_action) for the whole batch (model/ppo.py:57-82).  env.index is always 0."""
+    obs, goal, speed = state_list
+    v, a, logprob, mean = policy(obs, goal, speed)
+    lo = torch.as_tensor(action_bound[0], device=a.device, dtype=a.dtype)
+    hi = torch.as_tensor(action_bound[1], device=a.device, dtype=a.dtype)
+    scaled_action = torch.minimum(torch.maximum(a, lo), hi)        # np.clip (model/ppo.py:75)
+    return v, a, logprob, scaled_action
+
+
+def generate_action_no_sampling(env, state_list, policy, action_bound):
+    """(mean, scaled_action) (model/ppo.py:84-107)"""
+    obs, goal, speed = state_list
+    _, mean = policy.forward_values(obs.contiguous(), policy._pack_gs(goal, speed))
+    lo = torch.as_tensor(action_bound[0], device=mean.device, dtype=mean.dtype)
+    hi = torch.as_tensor(action_bound[1], device=mean.device, dtype=mean.dtype)
+    return mean, torch.minimum(torch.maximum(mean, lo), hi)
+
+
+def generate_train_data(rewards, gamma, values, last_value, dones, lam):
+    """GAE targets and advantages (model/ppo.py:122-139); (T,N) device tensors in, fp32 out."""
+    lib = _lib.load()
+    T, N = rewards.shape[0], rewards.shape[1]
+    dev = rewards.device
+    r = rewards.reshape(T, N).float().contiguous()
+    v = values.reshape(T, N).float().contiguous()
+    lv = last_value.reshape(N).float().contiguous()
+    d = dones.reshape(T, N).to(torch.uint8).contiguous()
+    targets = torch.empty(T, N, device=dev)
+    advs = torch.empty(T, N, device=dev)
+    _lib.check(lib.rlca_gae(_ptr(r), _ptr(v), _ptr(lv), _ptr(d), T, N, gamma, lam, _ptr(targets), _ptr(advs),
+                            _stream(dev)))
+    return targets, advs
+
+
+def normalize_advantages(advs, process_group=None):
+    """advs = (advs - advs.mean()) / advs.std() over the WHOLE rollout (model/ppo.py:148).  With a
+    process group the three moments are all-reduced so every rank normalises with the global statistics
+    (SURVEY.md §8(e))."""
+    lib = _lib.load()
+    dev = advs.device
+    x = advs.reshape(-1).float().contiguous()
+    mom = torch.empty(3, dtype=torch.float64, device=dev)
+    _lib.check(lib.rlca_adv_moments(_ptr(x), x.numel(), _ptr(mom), _stream(dev)))
+    if process_group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(mom, group=process_group if process_group is not True else None)
+    out = torch.empty_like(x)
+    _lib.check(lib.rlca_adv_apply(_ptr(x), x.numel(), _ptr(mom), _ptr(out), _stream(dev)))
+    return out.view(advs.shape)
+
+
+def _gather(lib, src, idx, row, dst, dev):
+    _lib.check(lib.rlca_gather_rows(_ptr(src), _ptr(idx), row, idx.numel(), _ptr(dst), _stream(dev)))
+
+
+def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_entropy, clip_value, num_step, num_env,
+                frames, obs_size, act_size, filter_index=None, drop_last=False, generator=None, process_group=None,
+                value_coef=20.0):
+    lib = _lib.load()
+    obss, goals, speeds, actions, logprobs, targets, values, rewards, advs = memory
+    dev = policy.device
+    advs = normalize_advantages(advs, process_group)
+    n_all = num_step * num_env
+    obss = obss.reshape(n_all, frames * obs_size).float().contiguous()
+    gs = torch.cat((goals.reshape(n_all, 2), speeds.reshape(n_all, 2)), dim=1).float().contiguous()
+    actions = actions.reshape(n_all, act_size).float().contiguous()
+    logprobs = logprobs.reshape(n_all).float().contiguous()
+    advs = advs.reshape(n_all).float().contiguous()
+    targets = targets.reshape(n_all).float().contiguous()
+    keep = torch.arange(n_all, device=dev)
+    if filter_index is not None and len(filter_index) > 0:      # np.delete(..., filter_index, 0) (model/ppo.py:212-218)
+        mask = torch.ones(n_all, dtype=torch.bool, device=dev)
+        mask[torch.as_tensor(list(filter_index), device=dev, dtype=torch.long)] = False
+        keep = keep[mask]
+    n = keep.numel()
+    world = 1
+    if process_group is not None:
+        import torch.distributed as dist
+        world = dist.get_world_size()
+    bs = batch_size
+    b_obs = torch.empty(bs, frames * obs_size, device=dev)
+    b_gs = torch.empty(bs, 4, device=dev)
+    b_act = torch.empty(bs, act_size, device=dev)
+    b_lp = torch.empty(bs, device=dev)
+    b_adv = torch.empty(bs, device=dev)
+    b_tgt = torch.empty(bs, device=dev)
+    v = torch.empty(bs, device=dev)
+    mean = torch.empty(bs, 2, device=dev)
+    nbatches = (n // bs) if drop_last else ((n + bs - 1) // bs)
+    log = torch.zeros(max(1, epoch * nbatches), 3, device=dev)
+    ws = policy._workspace(bs)
+    st = _stream(dev)
+    k = 0
+    for update in range(epoch):
+        perm = keep[torch.randperm(n, device=dev, generator=generator)]     # SubsetRandomSampler (model/ppo.py:159)
+        for bi in range(nbatches):
+            index = perm[bi * bs:(bi + 1) * bs].contiguous()
+            nb = index.numel()
+            _gather(lib, obss, index, frames * obs_size, b_obs, dev)
+            _gather(lib, gs, index, 4, b_gs, dev)
+            _gather(lib, actions, index, act_size, b_act, dev)
+            _gather(lib, logprobs, index, 1, b_lp, dev)
+            _gather(lib, advs, index, 1, b_adv, dev)
+            _gather(lib, targets, index, 1, b_tgt, dev)
+            _lib.check(lib.rlca_policy_forward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(v), _ptr(mean), st))
+            _lib.check(lib.rlca_ppo_loss_fwd_bwd(ws, _ptr(policy.flat), _ptr(v), _ptr(mean), _ptr(b_act), _ptr(b_lp),
+                                                 _ptr(b_adv), _ptr(b_tgt), nb, clip_value, coeff_entropy, value_coef,
+                                                 _ptr(log[k]), st))
+            _lib.check(lib.rlca_policy_backward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(policy.grad), st))
+            if process_group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(policy.grad, group=process_group if process_group is not True else None)
+            optimizer.step(grad_scale=1.0 / world)
+            k += 1
+    rows = log[:k].cpu().tolist()
+    for pl, vl, ent in rows:
+        logger_ppo.info('{}, {}, {}'.format(pl, vl, ent))
+    return rows
+
+
+def ppo_update_stage1(policy, optimizer, batch_size, memory, epoch, coeff_entropy=0.02, clip_value=0.2, num_step=2048,
+                      num_env=12, frames=1, obs_size=24, act_size=4, generator=None, process_group=None):
+    """model/ppo.py:143-194 (drop_last=False)."""
+    rows = _ppo_update(policy, optimizer, batch_size, memory, epoch, coeff_entropy, clip_value, num_step, num_env,
+                       frames, obs_size, act_size, None, False, generator, process_group)
+    print('update')
+    return rows
+
+
+def ppo_update_stage2(policy, optimizer, batch_size, memory, filter_index, epoch, coeff_entropy=0.02, clip_value=0.2,
+                      num_step=2048, num_env=12, frames=1, obs_size=24, act_size=4, generator=None, process_group=None):
+    """model/ppo.py:197-259 (filtered transitions deleted, drop_last=True)."""
+    rows = _ppo_update(policy, optimizer, batch_size, memory, epoch, coeff_entropy, clip_value, num_step, num_env,
+                       frames, obs_size, act_size, filter_index, True, generator, process_group)
+    print('filter {} transitions; update'.format(len(filter_index)))
+    return rows
