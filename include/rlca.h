@@ -78,7 +78,10 @@ typedef struct rlca_env_config {
     int32_t timeout;
     int32_t pre_distance_zero;
     int32_t scenario;
-    int32_t auto_reset;          /* done agents are re-spawned inside the step kernel */
+    int32_t auto_reset;          /* 0 = caller resets; 1 = a done agent is re-spawned inside the tick (stage 1,
+                                  * ppo_stage1.py:50-53); 2 = group-synchronous (stage 2): a done agent idles on its last
+                                  * command until every robot of its group (goal_tab[r][3] = group id) is done, then the
+                                  * whole group is re-spawned (ppo_stage2.py:72-84,105-106; model/utils.py:81-87) */
     int32_t max_reject;          /* cap on rejection-sampling tries */
     int32_t world_offset;        /* global index of this shard's first world (RNG keys are global) */
     uint64_t seed;
@@ -112,6 +115,8 @@ typedef struct rlca_step_io {
     uint8_t *flags_dev;
     float *gs_dev;
     float *eplog_dev;
+    const float *stack_in_dev;   /* optional (N,3,beams) scan FIFO (ppo_stage1.py:60,87-89): */
+    float *stack_out_dev;        /*   out = [in[1], in[2], new scan], or 3 x new scan after a re-spawn; both or neither */
 } rlca_step_io;
 
 typedef struct rlca_env rlca_env;
@@ -128,7 +133,7 @@ int rlca_env_set_map(rlca_env *env, const uint8_t *cells_host, int32_t grid_w, i
 
 /* Scenario tables (HOST pointers, robots_per_world rows of 4 floats):
  *   init_tab  x, y, theta, random_flag   (world-file agent poses / model/utils.py:6-25,41-53)
- *   goal_tab  gx, gy, random_flag, 0     (model/utils.py:27-38,55-63) */
+ *   goal_tab  gx, gy, random_flag, group id   (model/utils.py:27-38,55-63,83) */
 int rlca_env_set_tables(rlca_env *env, const float *init_tab_host, const float *goal_tab_host);
 
 /* reset_world (stage_world1.py:162-169 -> cb_reset_srv stageros.cpp:260-269) when

@@ -456,11 +456,13 @@ void orc_step(const orc_config *cfg, const uint8_t *static_cells,
 #pragma omp for schedule(dynamic, 1)
         for (int w = 0; w < cfg->num_worlds; ++w) {
             size_t base = (size_t)w * R;
+            int latch_in[ORC_MAX_ROBOTS];
+            for (int r = 0; r < R; ++r) latch_in[r] = meta[4 * (base + r) + 3];
             /* a1/a3: command + explicit-Euler diff-drive with the OLD heading (App. A.2) */
             for (int r = 0; r < R; ++r) {
                 size_t i = base + r;
                 float v, om;
-                if (live != NULL && !live[i]) { v = goal[4 * i + 2]; om = goal[4 * i + 3]; }
+                if ((live != NULL && !live[i]) || (cfg->auto_reset == 2 && latch_in[r])) { v = goal[4 * i + 2]; om = goal[4 * i + 3]; }
                 else {
                     v = action[2 * i + 0]; om = action[2 * i + 1];
                     if (!(fabsf(v) <= 3.0e38f)) v = 0.0f;   /* NaN/Inf guard */
@@ -491,6 +493,7 @@ void orc_step(const orc_config *cfg, const uint8_t *static_cells,
                 for (int k = 0; k < n; ++k)
                     if (grid_blocks(g, cfg, ox[k], oy[k], r)) { hit[r] = 1; break; }
             }
+            int done_r[ORC_MAX_ROBOTS], live_r[ORC_MAX_ROBOTS];
             for (int r = 0; r < R; ++r) {
                 size_t i = base + r;
                 float x0 = pose[4 * i + 0], y0 = pose[4 * i + 1], th0 = pose[4 * i + 2];
@@ -499,11 +502,9 @@ void orc_step(const orc_config *cfg, const uint8_t *static_cells,
                     else meta[4 * i + 2] = 0;
                 }
                 int is_live = (live == NULL) || live[i];
-                /* a6: GT velocity by finite difference (stageros.cpp:581-593), v=hypot (stage_world1.py:92-95) */
-                float vx = (nx[r] - x0) * cfg->inv_dt;
-                float vy = (ny[r] - y0) * cfg->inv_dt;
+                if (cfg->auto_reset == 2 && latch_in[r]) is_live = 0;     /* ppo_stage2.py:72-84 liveflag */
+                /* a6: GT velocity by finite difference (stageros.cpp:581-593) */
                 float w_gt = orc_normalize(nth[r] - th0) * cfg->inv_dt;
-                (void)vx; (void)vy;
                 pose[4 * i + 0] = nx[r]; pose[4 * i + 1] = ny[r]; pose[4 * i + 2] = nth[r];
                 float rew; int done = 0, result = 0;
                 int crashed = meta[4 * i + 2];
@@ -531,20 +532,33 @@ void orc_step(const orc_config *cfg, const uint8_t *static_cells,
                 flags[4 * i + 1] = (uint8_t)crashed;
                 flags[4 * i + 2] = (uint8_t)result;
                 flags[4 * i + 3] = 0;
+                done_r[r] = done; live_r[r] = is_live;
                 if (done && is_live) {
                     float *e = eplog + 8 * i;
                     e[0] = goal[4 * i + 0]; e[1] = goal[4 * i + 1]; e[2] = acc[4 * i + 0];
                     e[3] = (float)(meta[4 * i + 0] - 1);
                     e[4] = acc[4 * i + 2]; e[5] = acc[4 * i + 3]; e[6] = (float)result;
                     e[7] = (float)meta[4 * i + 1];
-                    if (cfg->auto_reset) {
-                        uint32_t gid = (uint32_t)((cfg->world_offset + w) * R + r);
-                        reset_agent(cfg, init_tab, goal_tab, gid, r, pose + 4 * i, goal + 4 * i,
-                                    acc + 4 * i, meta + 4 * i);
-                        nx[r] = pose[4 * i + 0]; ny[r] = pose[4 * i + 1]; nth[r] = pose[4 * i + 2];
-                        flags[4 * i + 3] = 1;
-                        rebuild = 1;
-                    }
+                }
+            }
+            /* re-spawn: immediately (stage 1, ppo_stage1.py:50-53) or once the whole group has terminated
+             * (stage 2: get_group_terminal, model/utils.py:81-87; ppo_stage2.py:105-106) */
+            for (int r = 0; r < R; ++r) {
+                size_t i = base + r;
+                int do_reset = 0;
+                if (cfg->auto_reset == 1) do_reset = done_r[r] && live_r[r];
+                else if (cfg->auto_reset == 2) {
+                    int gid = (int)goal_tab[4 * r + 3];
+                    do_reset = 1;
+                    for (int r2 = 0; r2 < R; ++r2)
+                        if ((int)goal_tab[4 * r2 + 3] == gid && !done_r[r2]) do_reset = 0;
+                }
+                if (do_reset) {
+                    uint32_t gid = (uint32_t)((cfg->world_offset + w) * R + r);
+                    reset_agent(cfg, init_tab, goal_tab, gid, r, pose + 4 * i, goal + 4 * i, acc + 4 * i, meta + 4 * i);
+                    nx[r] = pose[4 * i + 0]; ny[r] = pose[4 * i + 1]; nth[r] = pose[4 * i + 2];
+                    flags[4 * i + 3] = 1;
+                    rebuild = 1;
                 }
             }
             if (rebuild) build_grid(g, static_cells, cfg, nx, ny, nth);

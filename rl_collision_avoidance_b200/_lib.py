@@ -48,7 +48,7 @@ class EnvState(C.Structure):
 class StepIO(C.Structure):
     _fields_ = [('action_dev', C.c_void_p), ('live_dev', C.c_void_p), ('obs_dev', C.c_void_p),
                 ('reward_dev', C.c_void_p), ('flags_dev', C.c_void_p), ('gs_dev', C.c_void_p),
-                ('eplog_dev', C.c_void_p)]
+                ('eplog_dev', C.c_void_p), ('stack_in_dev', C.c_void_p), ('stack_out_dev', C.c_void_p)]
 
 
 # every symbol include/rlca.h declares: (name, restype, argtypes)

@@ -30,7 +30,7 @@ class Scenario:
     pre_distance_zero: int
     map: WorldMap
     init_tab: np.ndarray       # (R,4) x,y,theta,random_flag  float32
-    goal_tab: np.ndarray       # (R,4) gx,gy,random_flag,0    float32
+    goal_tab: np.ndarray       # (R,4) gx,gy,random_flag,group id   float32
     groups: tuple = ()         # stage-2 group boundaries (model/utils.py:83)
 
 
@@ -66,6 +66,9 @@ def make_scenario(name: str, map_: WorldMap | None = None, robots_per_world: int
         goal[:len(g), :2] = g
         init[34:44, 3] = 1.0                                  # stage_world2.py:211 random spawn
         goal[34:44, 2] = 1.0                                  # stage_world2.py:165 random goal
+        grp = t['groups']                                     # model/utils.py:83 group boundaries
+        for gi, (a, b) in enumerate(zip(grp[:-1], grp[1:])):
+            goal[a:b, 3] = gi
         return Scenario('stage2', 1, R, 200, 1.05, 1, m, init, goal, groups=tuple(t['groups']))
     if name == 'circle':
         m = map_ or load_map(os.path.join(ASSETS, 'circle_map.npz'))

@@ -88,10 +88,10 @@ class StageWorld:
         s = self._st[k]
         return _lib.EnvState(_ptr(s['pose']), _ptr(s['goal']), _ptr(s['acc']), _ptr(s['meta']))
 
-    def _io(self, action=None, live=None, obs=None):
+    def _io(self, action=None, live=None, obs=None, stack_in=None, stack_out=None):
         return _lib.StepIO(_ptr(action if action is not None else self._action), _ptr(live),
                            _ptr(obs if obs is not None else self.obs), _ptr(self.reward), _ptr(self.flags),
-                           _ptr(self.gs), _ptr(self.eplog))
+                           _ptr(self.gs), _ptr(self.eplog), _ptr(stack_in), _ptr(stack_out))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -143,7 +143,7 @@ class StageWorld:
         io = self._io(obs=obs)
         _lib.check(self.lib.rlca_env_observe(self._h, C.byref(st), C.byref(io), self._stream()))
 
-    def control_vel(self, action, live=None, obs_out=None):
+    def control_vel(self, action, live=None, obs_out=None, stack_in=None, stack_out=None):
         """Publish cmd_vel and advance one 0.1 s tick (stage_world1.py:226-234 + the
         rospy.sleep(0.001) of ppo_stage1.py:78).  `action` (N,2) device tensor (raw policy
         output; clipped to the action bound inside the kernel)."""
@@ -151,7 +151,7 @@ class StageWorld:
             else action.to(device=self.device, dtype=torch.float32).contiguous()
         lv = None if live is None else live.to(device=self.device, dtype=torch.uint8).contiguous()
         s_in, s_out = self._state_struct(self._cur), self._state_struct(1 - self._cur)
-        io = self._io(action=a, live=lv, obs=obs_out)
+        io = self._io(action=a, live=lv, obs=obs_out, stack_in=stack_in, stack_out=stack_out)
         self._keep = (a, lv)
         _lib.check(self.lib.rlca_env_step(self._h, C.byref(s_in), C.byref(s_out), C.byref(io), self._stream()))
         self._cur = 1 - self._cur
@@ -197,8 +197,8 @@ class StageWorld:
         self.generate_goal_point()
         return self.obs, self.get_local_goal(), self.get_self_speed()
 
-    def step(self, action, live=None, obs_out=None):
-        self.control_vel(action, live=live, obs_out=obs_out)
+    def step(self, action, live=None, obs_out=None, stack_in=None, stack_out=None):
+        self.control_vel(action, live=live, obs_out=obs_out, stack_in=stack_in, stack_out=stack_out)
         r, d, res = self.get_reward_and_terminate()
         return (self.obs if obs_out is None else obs_out), self.get_local_goal(), self.get_self_speed(), r, d, res
 

@@ -178,3 +178,55 @@ def test_errors_are_loud(built):
     with pytest.raises(_lib.RlcaError):
         env.raycast(torch.zeros(env.N, 4), normalise=False, out=None) if False else _lib.check(
             lib.rlca_raycast(env._h, None, None, 0, None))
+
+
+def test_group_synchronous_stage2_mode(built):
+    """auto_reset=2: finished robots idle until their whole group is done, then the group re-spawns
+    (ppo_stage2.py:72-84,105-106) — all inside the tick, bit-exact against the oracle."""
+    sc, env, orc = make_pair('stage2', num_worlds=2, auto_reset=2, seed=13)
+    env.reset_pose()
+    orc.reset_world()
+    orc.reset_pose()
+    rng = np.random.default_rng(21)
+    resets = idle = 0
+    for t in range(420):
+        a = random_actions(rng, orc.N)
+        env.control_vel(torch.from_numpy(a).cuda())
+        orc.step(a)
+        if t % 7 == 0 or t > 400:
+            assert_state_equal(env, orc, f'tick {t}')
+            assert_outputs_equal(env, orc, f'tick {t}')
+            assert np.array_equal(env.flags.cpu().numpy(), orc.flags)
+            assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), orc.reward.view(np.uint32))
+        resets += int(orc.flags[:, 3].sum())
+        idle += int((orc.meta[:, 3] != 0).sum())
+        # a group is re-spawned together: was_reset is constant inside every group
+        wr = orc.flags[:, 3].reshape(2, 44)
+        for a0, b0 in zip(sc.groups[:-1], sc.groups[1:]):
+            assert np.all(wr[:, a0:b0] == wr[:, a0:a0 + 1])
+    assert resets > 0 and idle > 0, (resets, idle)
+
+
+def test_fused_scan_fifo(built):
+    """stack_out = [stack_in[1], stack_in[2], scan] and three copies of the scan after a re-spawn
+    (the deque of ppo_stage1.py:60,87-89), written by the tick kernel itself."""
+    sc, env, orc = make_pair('stage1', num_worlds=3, auto_reset=1, seed=5)
+    env.reset_pose()
+    orc.reset_world()
+    orc.reset_pose()
+    N, B = orc.N, 512
+    ref = np.repeat(orc.obs[:, None, :], 3, axis=1).copy()
+    stacks = [torch.from_numpy(ref).cuda(), torch.empty(N, 3, B, device='cuda')]
+    rng = np.random.default_rng(2)
+    saw_reset = False
+    for t in range(200):
+        a = random_actions(rng, N)
+        env.control_vel(torch.from_numpy(a).cuda(), stack_in=stacks[t % 2], stack_out=stacks[(t + 1) % 2])
+        orc.step(a)
+        ref = np.stack([ref[:, 1], ref[:, 2], orc.obs], 1)
+        rs = orc.flags[:, 3] != 0
+        ref[rs] = orc.obs[rs][:, None, :]
+        saw_reset |= bool(rs.any())
+        if t % 9 == 0 or t == 199:
+            assert np.array_equal(stacks[(t + 1) % 2].cpu().numpy(), ref), f'tick {t}'
+    assert saw_reset
