@@ -140,26 +140,29 @@ class CNNPolicy:
         return torch.cat((goal, speed), dim=-1).contiguous()
 
     # ------------------------------------------------------------------ reference surface
-    def forward_values(self, x, gs):
-        """value (nb,1), mean (nb,2) without sampling; keeps activations for backward."""
+    def forward_values(self, x, gs, v_out=None, mean_out=None):
+        """value (nb,), mean (nb,2) without sampling; keeps activations for backward."""
         nb = x.shape[0]
         x = x.contiguous()
-        v = torch.empty(nb, device=self.device)
-        mean = torch.empty(nb, 2, device=self.device)
+        v = v_out if v_out is not None else torch.empty(nb, device=self.device)
+        mean = mean_out if mean_out is not None else torch.empty(nb, 2, device=self.device)
         _lib.check(self.lib.rlca_policy_forward(self._workspace(nb), _ptr(self.flat), _ptr(x), _ptr(gs), nb,
                                                 _ptr(v), _ptr(mean), self._stream()))
         return v, mean
 
-    def forward(self, x, goal, speed, gs=None):
-        """returns value estimation, action, log_action_prob, mean  (model/net.py:37-70)"""
+    def forward(self, x, goal, speed, gs=None, out=None):
+        """returns value estimation, action, log_action_prob, mean  (model/net.py:37-70).
+        `out` may hold preallocated 'value' (nb,), 'action' (nb,2), 'logprob' (nb,), 'scaled' (nb,2) tensors
+        (rollout slices); 'scaled' receives the clipped action of model/ppo.py:75."""
+        out = out or {}
         gs = gs if gs is not None else self._pack_gs(goal, speed)
-        v, mean = self.forward_values(x, gs)
+        v, mean = self.forward_values(x, gs, out.get('value'), out.get('mean'))
         nb = x.shape[0]
-        action = torch.empty(nb, 2, device=self.device)
-        logprob = torch.empty(nb, device=self.device)
+        action = out['action'] if 'action' in out else torch.empty(nb, 2, device=self.device)
+        logprob = out['logprob'] if 'logprob' in out else torch.empty(nb, device=self.device)
         self.sample_counter += 1
         _lib.check(self.lib.rlca_policy_sample(_ptr(self.flat), _ptr(mean), nb, self.sample_seed, self.sample_counter,
-                                               0, _ptr(action), _ptr(logprob), C.c_void_p(0), self._stream()))
+                                               0, _ptr(action), _ptr(logprob), _ptr(out.get('scaled')), self._stream()))
         return v.view(nb, 1), action, logprob.view(nb, 1), mean
 
     __call__ = forward

@@ -51,14 +51,20 @@ def transform_buffer(buff):
     return s_batch, goal_batch, speed_batch, a_batch, r_batch, d_batch, l_batch, v_batch
 
 
-def generate_action(env, state_list, policy, action_bound):
-    """(v, a, logprob, scaled_action) for the whole batch (model/ppo.py:57-82).  env.index is always 0."""
-    obs, goal, speed = state_list
-    v, a, logprob, mean = policy(obs, goal, speed)
-    lo = torch.as_tensor(action_bound[0], device=a.device, dtype=a.dtype)
-    hi = torch.as_tensor(action_bound[1], device=a.device, dtype=a.dtype)
-    scaled_action = torch.minimum(torch.maximum(a, lo), hi)        # np.clip (model/ppo.py:75)
-    return v, a, logprob, scaled_action
+def generate_action(env, state_list, policy, action_bound, out=None):
+    """(v, a, logprob, scaled_action) for the whole batch (model/ppo.py:57-82).  env.index is always 0.
+    state_list = (obs_stack (N,3,B), goal (N,2), speed (N,2)) or (obs_stack, gs (N,4)).  The clip to
+    action_bound [[0,-1],[1,1]] happens in the sampling kernel; `out` may hold rollout slices."""
+    assert list(map(float, action_bound[0])) == [0.0, -1.0] and list(map(float, action_bound[1])) == [1.0, 1.0], \
+        'the sampling kernel clips to the reference action bound (ppo_stage1.py:170)'
+    out = dict(out or {})
+    if 'scaled' not in out:
+        out['scaled'] = torch.empty(state_list[0].shape[0], 2, device=policy.device)
+    if len(state_list) == 2:
+        v, a, logprob, mean = policy.forward(state_list[0], None, None, gs=state_list[1], out=out)
+    else:
+        v, a, logprob, mean = policy.forward(state_list[0], state_list[1], state_list[2], out=out)
+    return v, a, logprob, out['scaled']
 
 
 def generate_action_no_sampling(env, state_list, policy, action_bound):

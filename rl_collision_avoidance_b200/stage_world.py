@@ -88,10 +88,12 @@ class StageWorld:
         s = self._st[k]
         return _lib.EnvState(_ptr(s['pose']), _ptr(s['goal']), _ptr(s['acc']), _ptr(s['meta']))
 
-    def _io(self, action=None, live=None, obs=None, stack_in=None, stack_out=None):
+    def _io(self, action=None, live=None, obs=None, stack_in=None, stack_out=None, out=None):
+        o = out or {}
         return _lib.StepIO(_ptr(action if action is not None else self._action), _ptr(live),
-                           _ptr(obs if obs is not None else self.obs), _ptr(self.reward), _ptr(self.flags),
-                           _ptr(self.gs), _ptr(self.eplog), _ptr(stack_in), _ptr(stack_out))
+                           _ptr(obs if obs is not None else self.obs), _ptr(o.get('reward', self.reward)),
+                           _ptr(o.get('flags', self.flags)), _ptr(o.get('gs', self.gs)),
+                           _ptr(o.get('eplog', self.eplog)), _ptr(stack_in), _ptr(stack_out))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -143,7 +145,7 @@ class StageWorld:
         io = self._io(obs=obs)
         _lib.check(self.lib.rlca_env_observe(self._h, C.byref(st), C.byref(io), self._stream()))
 
-    def control_vel(self, action, live=None, obs_out=None, stack_in=None, stack_out=None):
+    def control_vel(self, action, live=None, obs_out=None, stack_in=None, stack_out=None, out=None):
         """Publish cmd_vel and advance one 0.1 s tick (stage_world1.py:226-234 + the
         rospy.sleep(0.001) of ppo_stage1.py:78).  `action` (N,2) device tensor (raw policy
         output; clipped to the action bound inside the kernel)."""
@@ -151,15 +153,18 @@ class StageWorld:
             else action.to(device=self.device, dtype=torch.float32).contiguous()
         lv = None if live is None else live.to(device=self.device, dtype=torch.uint8).contiguous()
         s_in, s_out = self._state_struct(self._cur), self._state_struct(1 - self._cur)
-        io = self._io(action=a, live=lv, obs=obs_out, stack_in=stack_in, stack_out=stack_out)
+        io = self._io(action=a, live=lv, obs=obs_out, stack_in=stack_in, stack_out=stack_out, out=out)
         self._keep = (a, lv)
+        self._last_out = out or {}
         _lib.check(self.lib.rlca_env_step(self._h, C.byref(s_in), C.byref(s_out), C.byref(io), self._stream()))
         self._cur = 1 - self._cur
 
     def get_reward_and_terminate(self, t=None):
         """(reward, terminate, result) of the tick just run (stage_world1.py:180-211).  The step
         counter lives on the device (state meta[:,0]); `t` is accepted for signature parity."""
-        return self.reward, self.flags[:, 0].bool(), self.flags[:, 2]
+        o = getattr(self, '_last_out', {})
+        flags = o.get('flags', self.flags)
+        return o.get('reward', self.reward), flags[:, 0].bool(), flags[:, 2]
 
     def get_laser_observation(self):
         return self.obs
