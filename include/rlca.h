@@ -199,6 +199,9 @@ typedef struct rlca_policy rlca_policy;   /* workspace (activations kept for bac
 int64_t rlca_policy_param_offset(int32_t tensor_index);
 int64_t rlca_policy_param_size(int32_t tensor_index);     /* unpadded element count of tensor i */
 int64_t rlca_policy_launch_count(const rlca_policy *pol);
+/* fc1 forward/backward GEMMs on the tcgen05 tensor cores with 3xTF32 error compensation (default on);
+ * 0 selects the plain fp32 CUDA-core GEMM (kept as the cross-check for the tensor-core path). */
+int rlca_policy_set_tensor_cores(rlca_policy *pol, int32_t enable);
 
 /* Workspace sized for batches up to max_batch rows. */
 int rlca_policy_create(int32_t max_batch, rlca_policy **out);

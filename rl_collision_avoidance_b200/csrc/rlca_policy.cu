@@ -16,6 +16,7 @@
 
 #include "../../include/rlca.h"
 #include "rlca_common.cuh"
+#include "rlca_gemm_tc.cuh"
 
 // ------------------------------------------------------------------------------------ layout
 static const int64_t kTensorSize[RLCA_POLICY_NTENSORS] = {
@@ -87,6 +88,16 @@ struct rlca_policy {
     float *part;     // [2][B][CONV_PART]
     float *headpart; // [chunks][3][128 + 4]
     float *red;      // small reduction scratch (64 floats)
+    // ---- tensor-core (3xTF32) path for fc1: hi/lo splits of the operands, all K-major
+    int use_tc;
+    int bpad;        // max_batch rounded up to 32 (row pitch of the transposed operands)
+    float *Fs;       // [2 towers][hi,lo][B][4096]
+    float *W1s;      // [2][hi,lo][256][4096]
+    float *W1Ts;     // [2][hi,lo][4096][256]
+    float *dZs;      // [2][hi,lo][B][256]
+    float *dZTs;     // [2][hi,lo][256][bpad]
+    float *FTs;      // [2][hi,lo][4096][bpad]
+    float *P;        // split-K partials [splits<=8][2][B][256]
     int64_t launches;
 };
 
@@ -867,6 +878,20 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
     RLCA_CUDA_TRY(cudaMalloc(&p->part, 2 * B * CONV_PART * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->headpart, (size_t)chunks * 3 * 132 * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->red, 64 * sizeof(float)));
+    p->bpad = (max_batch + 31) / 32 * 32;
+    {
+        const size_t BP = (size_t)p->bpad;
+        RLCA_CUDA_TRY(cudaMalloc(&p->Fs, 4 * B * FEAT * sizeof(float)));
+        RLCA_CUDA_TRY(cudaMalloc(&p->W1s, 4 * (size_t)256 * FEAT * sizeof(float)));
+        RLCA_CUDA_TRY(cudaMalloc(&p->W1Ts, 4 * (size_t)256 * FEAT * sizeof(float)));
+        RLCA_CUDA_TRY(cudaMalloc(&p->dZs, 4 * B * 256 * sizeof(float)));
+        RLCA_CUDA_TRY(cudaMalloc(&p->dZTs, 4 * 256 * BP * sizeof(float)));
+        RLCA_CUDA_TRY(cudaMalloc(&p->FTs, 4 * (size_t)FEAT * BP * sizeof(float)));
+        RLCA_CUDA_TRY(cudaMalloc(&p->P, 8 * 2 * B * 256 * sizeof(float)));
+        int rc = rlca_tc_init();
+        if (rc) return rc;
+        p->use_tc = 1;
+    }
     RLCA_CUDA_TRY(cudaFuncSetAttribute(conv_tower_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ConvSmem)));
     RLCA_CUDA_TRY(cudaFuncSetAttribute(conv_tower_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -880,11 +905,19 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
     if (!p) return RLCA_OK;
     cudaFree(p->F); cudaFree(p->X); cudaFree(p->H2); cudaFree(p->dOut); cudaFree(p->dZ2); cudaFree(p->dX);
     cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red);
+    cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P);
     delete p;
     return RLCA_OK;
 }
 
 extern "C" int64_t rlca_policy_launch_count(const rlca_policy *p) { return p ? p->launches : -1; }
+
+extern "C" int rlca_policy_set_tensor_cores(rlca_policy *p, int32_t enable)
+{
+    if (!p) return rlca_set_err(RLCA_ERR_INVALID, "policy is NULL");
+    p->use_tc = enable ? 1 : 0;
+    return RLCA_OK;
+}
 
 extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const float *obs, const float *gs, int32_t nb,
                                    float *value, float *mean, void *stream)
@@ -895,11 +928,37 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
     const TowerPtrs ta = tower_ptrs(params, 0), tc = tower_ptrs(params, 1);
     conv_tower_fwd_kernel<<<nb, 256, sizeof(ConvSmem), s>>>(obs, ta, tc, pol->F, nb);
     GemmArgs g{};
-    // fc1: X[:, :256] = relu(F W1^T + b1)
-    g.M = nb; g.N = 256; g.K = FEAT; g.lda = FEAT; g.ldb = FEAT; g.ldc = XLD; g.relu = 1;
-    g.pr[0] = GemmProblem{pol->F, ta.fc1w, ta.fc1b, nullptr, pol->X};
-    g.pr[1] = GemmProblem{pol->F + (size_t)nb * FEAT, tc.fc1w, tc.fc1b, nullptr, pol->X + (size_t)nb * XLD};
-    launch_gemm<false, true>(g, 2, s);
+    if (pol->use_tc) {
+        // fc1 on the tensor cores: split F and W1 into tf32 hi/lo parts, split-K 3xTF32 GEMM, fused bias+ReLU reduce
+        const size_t B = (size_t)nb;
+        const size_t WSZ = (size_t)256 * FEAT;
+        RlcaTcProblem pr[2];
+        for (int t = 0; t < 2; ++t) {
+            float *Fh = pol->Fs + (size_t)(2 * t) * B * FEAT, *Fl = Fh + B * FEAT;
+            float *Wh = pol->W1s + (size_t)(2 * t) * WSZ, *Wl = Wh + WSZ;
+            const float *w = t == 0 ? ta.fc1w : tc.fc1w;
+            rlca_tc_split(pol->F + (size_t)t * B * FEAT, nb, FEAT, FEAT, Fh, Fl, FEAT, s);
+            rlca_tc_split(w, 256, FEAT, FEAT, Wh, Wl, FEAT, s);
+            rlca_tc_transpose_split(w, 256, FEAT, FEAT, pol->W1Ts + (size_t)(2 * t) * WSZ, pol->W1Ts + (size_t)(2 * t + 1) * WSZ,
+                                    256, s);
+            pr[t] = RlcaTcProblem{Fh, Fl, Wh, Wl, FEAT, FEAT, pol->P + (size_t)t * B * 256, nullptr};
+        }
+        const int mtiles = (nb + 127) / 128;
+        int splits = 1;
+        while (splits < 8 && mtiles * 2 * 2 * splits < 120) splits *= 2;
+        const long long split_stride = 2LL * nb * 256;
+        int rc = rlca_tc_gemm(pr, 2, nb, 256, FEAT, 256, splits, split_stride, s);
+        if (rc) return rc;
+        rlca_tc_splitk_bias_relu(pol->P, splits, split_stride, (long long)nb * 256, ta.fc1b, tc.fc1b, nb, 256, pol->X,
+                                 pol->X + (size_t)nb * XLD, XLD, s);
+        pol->launches += 8;
+    } else {
+        // fc1: X[:, :256] = relu(F W1^T + b1)
+        g.M = nb; g.N = 256; g.K = FEAT; g.lda = FEAT; g.ldb = FEAT; g.ldc = XLD; g.relu = 1;
+        g.pr[0] = GemmProblem{pol->F, ta.fc1w, ta.fc1b, nullptr, pol->X};
+        g.pr[1] = GemmProblem{pol->F + (size_t)nb * FEAT, tc.fc1w, tc.fc1b, nullptr, pol->X + (size_t)nb * XLD};
+        launch_gemm<false, true>(g, 2, s);
+    }
     fill_gs_kernel<<<(nb + 127) / 128, 128, 0, s>>>(pol->X, gs, nb);
     // fc2: H2 = relu(X W2^T + b2)
     g.M = nb; g.N = 128; g.K = XLD; g.lda = XLD; g.ldb = XLD; g.ldc = 128; g.relu = 1;
@@ -981,6 +1040,31 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     cs.A[0] = pol->dX; cs.A[1] = pol->dX + B * XLD; cs.out[0] = ga.fc1b; cs.out[1] = gc.fc1b;
     cs.rows = nb; cs.cols = 256; cs.ld = XLD;
     colsum_kernel<<<dim3(8, 2), 256, 0, s>>>(cs);
+    if (pol->use_tc) {
+        // both fc1 gradient GEMMs on the tensor cores (operands made K-major by transpose+split kernels)
+        const size_t WSZ = (size_t)256 * FEAT;
+        const size_t BP = (size_t)((nb + 31) / 32 * 32);
+        RlcaTcProblem pw[2], pf[2];
+        for (int t = 0; t < 2; ++t) {
+            const float *dz = pol->dX + (size_t)t * B * XLD;                       // dZ1 [nb,256], pitch 260
+            float *dzh = pol->dZs + (size_t)(2 * t) * B * 256, *dzl = dzh + B * 256;
+            float *dzth = pol->dZTs + (size_t)(2 * t) * 256 * BP, *dztl = dzth + 256 * BP;
+            float *fth = pol->FTs + (size_t)(2 * t) * FEAT * BP, *ftl = fth + FEAT * BP;
+            rlca_tc_split(dz, nb, 256, XLD, dzh, dzl, 256, s);
+            rlca_tc_transpose_split(dz, nb, 256, XLD, dzth, dztl, (int)BP, s);
+            rlca_tc_transpose_split(pol->F + (size_t)t * B * FEAT, nb, FEAT, FEAT, fth, ftl, (int)BP, s);
+            // dW_fc1 (256 x 4096) = dZ1^T F : A = dZ1^T [256, nb], B = F^T [4096, nb]
+            pw[t] = RlcaTcProblem{dzth, dztl, fth, ftl, (int)BP, (int)BP, t == 0 ? ga.fc1w : gc.fc1w, nullptr};
+            // dF (nb x 4096) = dZ1 W_fc1 : A = dZ1 [nb,256], B = W1^T [4096,256]; masked by relu(conv2)
+            pf[t] = RlcaTcProblem{dzh, dzl, pol->W1Ts + (size_t)(2 * t) * WSZ, pol->W1Ts + (size_t)(2 * t + 1) * WSZ, 256, 256,
+                                  pol->dF + (size_t)t * B * FEAT, pol->F + (size_t)t * B * FEAT};
+        }
+        int rc = rlca_tc_gemm(pw, 2, 256, FEAT, nb, FEAT, 1, 0, s);
+        if (rc) return rc;
+        rc = rlca_tc_gemm(pf, 2, nb, FEAT, 256, FEAT, 1, 0, s);
+        if (rc) return rc;
+        pol->launches += 8;
+    } else {
     // dW_fc1 (256 x 4096) = dZ1^T F
     g.M = 256; g.N = FEAT; g.K = nb; g.lda = XLD; g.ldb = FEAT; g.ldc = FEAT; g.relu = 0;
     g.pr[0] = GemmProblem{pol->dX, pol->F, nullptr, nullptr, ga.fc1w};
@@ -991,6 +1075,7 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     g.pr[0] = GemmProblem{pol->dX, ta.fc1w, nullptr, pol->F, pol->dF};
     g.pr[1] = GemmProblem{pol->dX + B * XLD, tc.fc1w, nullptr, pol->F + B * FEAT, pol->dF + B * FEAT};
     launch_gemm<false, false>(g, 2, s);
+    }
     conv_tower_bwd_kernel<<<dim3(nb, 2), 256, sizeof(ConvBwdSmem), s>>>(obs, ta, tc, pol->dF, pol->part, nb);
     conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->part, nb, ga, gc);
     pol->launches += 10;

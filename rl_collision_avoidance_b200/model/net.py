@@ -67,6 +67,7 @@ class CNNPolicy:
         self.max_batch = max_batch
         self.sample_seed = 0 if seed is None else int(seed)
         self.sample_counter = 0
+        self.tensor_cores = True
         self.reset_parameters(seed)
 
     # ------------------------------------------------------------------ parameters
@@ -123,7 +124,14 @@ class CNNPolicy:
             torch.cuda.set_device(self.device)
             _lib.check(self.lib.rlca_policy_create(cap, C.byref(h)))
             self._ws, self._ws_batch = h, cap
+            _lib.check(self.lib.rlca_policy_set_tensor_cores(self._ws, int(self.tensor_cores)))
         return self._ws
+
+    def set_tensor_cores(self, enable=True):
+        """fc1 GEMMs on tcgen05 with 3xTF32 compensation (default) or on the fp32 CUDA-core GEMM."""
+        self.tensor_cores = bool(enable)
+        if self._ws is not None:
+            _lib.check(self.lib.rlca_policy_set_tensor_cores(self._ws, int(self.tensor_cores)))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
