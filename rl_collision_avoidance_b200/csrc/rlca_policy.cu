@@ -74,6 +74,7 @@ static TowerGrads tower_grads(float *p, int tower)
 
 #define FEAT 4096
 #define XLD 260          // fc2 input: 256 fc1 outputs + goal(2) + speed(2)
+#define RSPLIT 16        // row/K splits of the small batch reductions (two-stage, deterministic)
 #define CONV_PART 3616   // per-(sample,tower) conv gradient partials: cv2w 3072 | cv2b 32 | cv1w 480 | cv1b 32
 
 struct rlca_policy {
@@ -88,6 +89,7 @@ struct rlca_policy {
     float *part;     // [2][B][CONV_PART]
     float *headpart; // [chunks][3][128 + 4]
     float *red;      // small reduction scratch (64 floats)
+    float *S;        // split-reduction scratch: [RSPLIT][2][max(CONV_PART, 128*260)]
     // ---- tensor-core (3xTF32) path for fc1: hi/lo splits of the operands, all K-major
     int use_tc;
     int bpad;        // max_batch rounded up to 32 (row pitch of the transposed operands)
@@ -368,19 +370,30 @@ __global__ void __launch_bounds__(256) conv_tower_bwd_kernel(const float *__rest
 }
 
 // sum the per-sample conv partials over the batch: grid (ceil(CONV_PART/256), 2)
-__global__ void conv_part_reduce_kernel(const float *__restrict__ part, int nb, TowerGrads ga, TowerGrads gc)
+__global__ void conv_part_reduce_kernel(const float *__restrict__ part, int nb, float *__restrict__ P)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
     if (j >= CONV_PART) return;
+    const int nper = (nb + gridDim.z - 1) / gridDim.z;
+    const int nbeg = blockIdx.z * nper, nend = min(nb, nbeg + nper);
     const float *src = part + (size_t)t * nb * CONV_PART + j;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int n = 0;
+    int n = nbeg;
+    nb = nend;
     for (; n + 3 < nb; n += 4) {
         a0 += src[(size_t)(n + 0) * CONV_PART]; a1 += src[(size_t)(n + 1) * CONV_PART];
         a2 += src[(size_t)(n + 2) * CONV_PART]; a3 += src[(size_t)(n + 3) * CONV_PART];
     }
     for (; n < nb; ++n) a0 += src[(size_t)n * CONV_PART];
-    const float v = (a0 + a1) + (a2 + a3);
+    P[((size_t)blockIdx.z * 2 + t) * CONV_PART + j] = (a0 + a1) + (a2 + a3);
+}
+
+__global__ void conv_part_final_kernel(const float *__restrict__ P, int splits, TowerGrads ga, TowerGrads gc)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (j >= CONV_PART) return;
+    float v = 0.f;
+    for (int sidx = 0; sidx < splits; ++sidx) v += P[((size_t)sidx * 2 + t) * CONV_PART + j];
     const TowerGrads &g = t == 0 ? ga : gc;
     if (j < 3072) g.cv2w[j] = v;
     else if (j < 3104) g.cv2b[j - 3072] = v;
@@ -401,6 +414,8 @@ struct GemmArgs {
     GemmProblem pr[2];
     int M, N, K, lda, ldb, ldc;
     int relu;
+    int ksplit;               // > 1: blockIdx.z = problem * ksplit + split; raw partials to C + split * split_stride
+    long long split_stride;
 };
 
 template <bool TA, bool TB>
@@ -408,7 +423,11 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
 {
     __shared__ __align__(16) float As[16][64 + 4];
     __shared__ __align__(16) float Bs[16][64 + 4];
-    const GemmProblem pr = blockIdx.z ? g.pr[1] : g.pr[0];
+    const int ks = g.ksplit > 1 ? g.ksplit : 1;
+    const int prob = blockIdx.z / ks, split = blockIdx.z - prob * ks;
+    const GemmProblem pr = prob ? g.pr[1] : g.pr[0];
+    const int kper = ((g.K + ks - 1) / ks + 15) / 16 * 16;
+    const int kbeg = split * kper, kend = min(g.K, kbeg + kper);
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     const int tx = tid & 15, ty = tid >> 4;
@@ -417,7 +436,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    for (int k0 = 0; k0 < g.K; k0 += 16) {
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
         // ---- A tile -> As[k][m]
         if (!TA) {
             const int m = tid >> 2, kq = (tid & 3) * 4;            // 64 rows x 4 float4 along k
@@ -425,11 +444,11 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gm < g.M) {
                 const float *src = pr.A + (size_t)gm * g.lda + gk;
-                if (gk + 3 < g.K) v = *reinterpret_cast<const float4 *>(src);
+                if (gk + 3 < kend) v = *reinterpret_cast<const float4 *>(src);
                 else {
-                    if (gk + 0 < g.K) v.x = src[0];
-                    if (gk + 1 < g.K) v.y = src[1];
-                    if (gk + 2 < g.K) v.z = src[2];
+                    if (gk + 0 < kend) v.x = src[0];
+                    if (gk + 1 < kend) v.y = src[1];
+                    if (gk + 2 < kend) v.z = src[2];
                 }
             }
             As[kq + 0][m] = v.x; As[kq + 1][m] = v.y; As[kq + 2][m] = v.z; As[kq + 3][m] = v.w;
@@ -437,7 +456,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
             const int k = tid >> 4, mq = (tid & 15) * 4;           // 16 k x 16 float4 along m
             const int gk = k0 + k, gm = m0 + mq;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gk < g.K) {
+            if (gk < kend) {
                 const float *src = pr.A + (size_t)gk * g.lda + gm;
                 if (gm + 3 < g.M) v = *reinterpret_cast<const float4 *>(src);
                 else {
@@ -455,11 +474,11 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gn < g.N) {
                 const float *src = pr.B + (size_t)gn * g.ldb + gk;
-                if (gk + 3 < g.K) v = *reinterpret_cast<const float4 *>(src);
+                if (gk + 3 < kend) v = *reinterpret_cast<const float4 *>(src);
                 else {
-                    if (gk + 0 < g.K) v.x = src[0];
-                    if (gk + 1 < g.K) v.y = src[1];
-                    if (gk + 2 < g.K) v.z = src[2];
+                    if (gk + 0 < kend) v.x = src[0];
+                    if (gk + 1 < kend) v.y = src[1];
+                    if (gk + 2 < kend) v.z = src[2];
                 }
             }
             Bs[kq + 0][n] = v.x; Bs[kq + 1][n] = v.y; Bs[kq + 2][n] = v.z; Bs[kq + 3][n] = v.w;
@@ -467,7 +486,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
             const int k = tid >> 4, nq = (tid & 15) * 4;
             const int gk = k0 + k, gn = n0 + nq;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gk < g.K) {
+            if (gk < kend) {
                 const float *src = pr.B + (size_t)gk * g.ldb + gn;
                 if (gn + 3 < g.N) v = *reinterpret_cast<const float4 *>(src);
                 else {
@@ -500,6 +519,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
             const int gn = n0 + tx * 4 + j;
             if (gn >= g.N) continue;
             float v = acc[i][j];
+            if (ks > 1) { pr.C[(size_t)split * g.split_stride + (size_t)gm * g.ldc + gn] = v; continue; }
             if (pr.bias) v += pr.bias[gn];
             if (g.relu) v = fmaxf(v, 0.0f);
             if (pr.mask) v = pr.mask[(size_t)gm * g.ldc + gn] > 0.0f ? v : 0.0f;
@@ -511,8 +531,18 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
 template <bool TA, bool TB>
 static void launch_gemm(const GemmArgs &g, int nprob, cudaStream_t s)
 {
-    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, nprob);
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, nprob * (g.ksplit > 1 ? g.ksplit : 1));
     gemm_kernel<TA, TB><<<grid, 256, 0, s>>>(g);
+}
+
+// out_t[j] = sum_s P[(s * 2 + t) * n + j]  (deterministic second stage of every split reduction); grid (ceil(n/256), 2)
+__global__ void reduce_splits_kernel(const float *__restrict__ P, int splits, int n, float *out0, float *out1)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (j >= n) return;
+    float acc = 0.f;
+    for (int sidx = 0; sidx < splits; ++sidx) acc += P[((size_t)sidx * 2 + t) * n + j];
+    (t ? out1 : out0)[j] = acc;
 }
 
 // ------------------------------------------------------------------------------------ small kernels
@@ -555,8 +585,9 @@ __global__ void heads_fwd_kernel(const float *__restrict__ H2, const float *__re
     }
 }
 
+#define HEAD_CHUNK 8
 // dZ2[t][i][j] for both towers + per-chunk partial sums of the three head weight/bias gradients.
-// block = 128 threads (one per hidden unit j), grid = chunks of 32 samples.
+// block = 128 threads (one per hidden unit j), grid = chunks of HEAD_CHUNK samples.
 __global__ void __launch_bounds__(128) heads_bwd_kernel(const float *__restrict__ H2, const float *__restrict__ dOut,
                                                         const float *__restrict__ a1w, const float *__restrict__ a2w,
                                                         const float *__restrict__ cw, int nb, float *__restrict__ dZ2,
@@ -565,8 +596,8 @@ __global__ void __launch_bounds__(128) heads_bwd_kernel(const float *__restrict_
     const int j = threadIdx.x, c = blockIdx.x;
     const float w1 = a1w[j], w2 = a2w[j], w3 = cw[j];
     float g1 = 0.f, g2 = 0.f, g3 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-    const int i1 = min(nb, (c + 1) * 32);
-    for (int i = c * 32; i < i1; ++i) {
+    const int i1 = min(nb, (c + 1) * HEAD_CHUNK);
+    for (int i = c * HEAD_CHUNK; i < i1; ++i) {
         const float4 d = reinterpret_cast<const float4 *>(dOut)[i];     // dv, dz1, dz2, _
         const float ha = H2[(size_t)i * 128 + j], hc = H2[((size_t)nb + i) * 128 + j];
         dZ2[(size_t)i * 128 + j] = ha > 0.0f ? fmaf(d.y, w1, d.z * w2) : 0.0f;
@@ -591,22 +622,24 @@ __global__ void heads_part_reduce_kernel(const float *__restrict__ headpart, int
 }
 
 // out[t][j] = sum_i A[t][i*ld + j] ; grid (ceil(ncols/32), ntowers), 256 threads = 8 row groups x 32 columns
-struct ColsumArgs { const float *A[2]; float *out[2]; int rows, cols, ld; };
+struct ColsumArgs { const float *A[2]; float *P; int rows, cols, ld; };
 __global__ void __launch_bounds__(256) colsum_kernel(const ColsumArgs a)
 {
     __shared__ float red[8][33];
     const int t = blockIdx.y, lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
     float acc = 0.f;
+    const int rper = (a.rows + gridDim.z - 1) / gridDim.z;
+    const int r0 = blockIdx.z * rper, r1 = min(a.rows, r0 + rper);
     if (j < a.cols)
-        for (int i = rg; i < a.rows; i += 8) acc += a.A[t][(size_t)i * a.ld + j];
+        for (int i = r0 + rg; i < r1; i += 8) acc += a.A[t][(size_t)i * a.ld + j];
     red[rg][lane] = acc;
     __syncthreads();
     if (rg == 0 && j < a.cols) {
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < 8; ++r) s += red[r][lane];
-        a.out[t][j] = s;
+        a.P[((size_t)blockIdx.z * 2 + t) * a.cols + j] = s;
     }
 }
 
@@ -867,7 +900,7 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
     memset(p, 0, sizeof(*p));
     p->max_batch = max_batch;
     const size_t B = (size_t)max_batch;
-    const int chunks = (max_batch + 31) / 32;
+    const int chunks = (max_batch + HEAD_CHUNK - 1) / HEAD_CHUNK;
     RLCA_CUDA_TRY(cudaMalloc(&p->F, 2 * B * FEAT * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->X, 2 * B * XLD * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->H2, 2 * B * 128 * sizeof(float)));
@@ -878,6 +911,7 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
     RLCA_CUDA_TRY(cudaMalloc(&p->part, 2 * B * CONV_PART * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->headpart, (size_t)chunks * 3 * 132 * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->red, 64 * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->S, (size_t)RSPLIT * 2 * 128 * XLD * sizeof(float)));
     p->bpad = (max_batch + 31) / 32 * 32;
     {
         const size_t BP = (size_t)p->bpad;
@@ -904,7 +938,7 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
 {
     if (!p) return RLCA_OK;
     cudaFree(p->F); cudaFree(p->X); cudaFree(p->H2); cudaFree(p->dOut); cudaFree(p->dZ2); cudaFree(p->dX);
-    cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red);
+    cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red); cudaFree(p->S);
     cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P);
     delete p;
     return RLCA_OK;
@@ -1012,7 +1046,7 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     // padding floats between tensors must stay zero for the optimizer / all-reduce
     RLCA_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)tensor_offset(RLCA_POLICY_NTENSORS), s));
     RLCA_CUDA_TRY(cudaMemcpyAsync(grads + tensor_offset(T_LOGSTD), pol->red, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    const int chunks = (nb + 31) / 32;
+    const int chunks = (nb + HEAD_CHUNK - 1) / HEAD_CHUNK;
     heads_bwd_kernel<<<chunks, 128, 0, s>>>(pol->H2, pol->dOut, params + tensor_offset(T_A1W),
                                             params + tensor_offset(T_A2W), params + tensor_offset(T_CRITW), nb, pol->dZ2,
                                             pol->headpart);
@@ -1022,24 +1056,29 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
                                                grads + tensor_offset(T_CRITB));
     // fc2 bias grads
     ColsumArgs cs{};
-    cs.A[0] = pol->dZ2; cs.A[1] = pol->dZ2 + B * 128; cs.out[0] = ga.fc2b; cs.out[1] = gc.fc2b;
+    cs.A[0] = pol->dZ2; cs.A[1] = pol->dZ2 + B * 128; cs.P = pol->S;
     cs.rows = nb; cs.cols = 128; cs.ld = 128;
-    colsum_kernel<<<dim3(4, 2), 256, 0, s>>>(cs);
+    colsum_kernel<<<dim3(4, 2, RSPLIT), 256, 0, s>>>(cs);
+    reduce_splits_kernel<<<dim3(1, 2), 256, 0, s>>>(pol->S, RSPLIT, 128, ga.fc2b, gc.fc2b);
     GemmArgs g{};
     // dW_fc2 (128 x 260) = dZ2^T X
     g.M = 128; g.N = XLD; g.K = nb; g.lda = 128; g.ldb = XLD; g.ldc = XLD; g.relu = 0;
-    g.pr[0] = GemmProblem{pol->dZ2, pol->X, nullptr, nullptr, ga.fc2w};
-    g.pr[1] = GemmProblem{pol->dZ2 + B * 128, pol->X + B * XLD, nullptr, nullptr, gc.fc2w};
+    g.ksplit = RSPLIT; g.split_stride = 2LL * 128 * XLD;       // partial P[(split*2 + tower)][128][260]
+    g.pr[0] = GemmProblem{pol->dZ2, pol->X, nullptr, nullptr, pol->S};
+    g.pr[1] = GemmProblem{pol->dZ2 + B * 128, pol->X + B * XLD, nullptr, nullptr, pol->S + 128 * XLD};
     launch_gemm<true, false>(g, 2, s);
+    reduce_splits_kernel<<<dim3((128 * XLD + 255) / 256, 2), 256, 0, s>>>(pol->S, RSPLIT, 128 * XLD, ga.fc2w, gc.fc2w);
+    g.ksplit = 0; g.split_stride = 0;
     // dX (nb x 260) = dZ2 W_fc2, masked by relu(fc1) (columns 256..259 = goal/speed carry no parameter gradient)
     g.M = nb; g.N = 256; g.K = 128; g.lda = 128; g.ldb = XLD; g.ldc = XLD; g.relu = 0;
     g.pr[0] = GemmProblem{pol->dZ2, ta.fc2w, nullptr, pol->X, pol->dX};
     g.pr[1] = GemmProblem{pol->dZ2 + B * 128, tc.fc2w, nullptr, pol->X + B * XLD, pol->dX + B * XLD};
     launch_gemm<false, false>(g, 2, s);
     // fc1 bias grads
-    cs.A[0] = pol->dX; cs.A[1] = pol->dX + B * XLD; cs.out[0] = ga.fc1b; cs.out[1] = gc.fc1b;
+    cs.A[0] = pol->dX; cs.A[1] = pol->dX + B * XLD; cs.P = pol->S;
     cs.rows = nb; cs.cols = 256; cs.ld = XLD;
-    colsum_kernel<<<dim3(8, 2), 256, 0, s>>>(cs);
+    colsum_kernel<<<dim3(8, 2, RSPLIT), 256, 0, s>>>(cs);
+    reduce_splits_kernel<<<dim3(1, 2), 256, 0, s>>>(pol->S, RSPLIT, 256, ga.fc1b, gc.fc1b);
     if (pol->use_tc) {
         // both fc1 gradient GEMMs on the tensor cores (operands made K-major by transpose+split kernels)
         const size_t WSZ = (size_t)256 * FEAT;
@@ -1077,7 +1116,8 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     launch_gemm<false, false>(g, 2, s);
     }
     conv_tower_bwd_kernel<<<dim3(nb, 2), 256, sizeof(ConvBwdSmem), s>>>(obs, ta, tc, pol->dF, pol->part, nb);
-    conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->part, nb, ga, gc);
+    conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(pol->part, nb, pol->S);
+    conv_part_final_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->S, RSPLIT, ga, gc);
     pol->launches += 10;
     RLCA_CUDA_TRY(cudaGetLastError());
     return RLCA_OK;

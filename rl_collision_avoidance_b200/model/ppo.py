@@ -102,8 +102,8 @@ def normalize_advantages(advs, process_group=None):
     mom = torch.empty(3, dtype=torch.float64, device=dev)
     _lib.check(lib.rlca_adv_moments(_ptr(x), x.numel(), _ptr(mom), _stream(dev)))
     if process_group is not None:
-        import torch.distributed as dist
-        dist.all_reduce(mom, group=process_group if process_group is not True else None)
+        from ..parallel import allreduce_moments
+        allreduce_moments(mom, None if process_group is True else process_group)
     out = torch.empty_like(x)
     _lib.check(lib.rlca_adv_apply(_ptr(x), x.numel(), _ptr(mom), _ptr(out), _stream(dev)))
     return out.view(advs.shape)
@@ -168,8 +168,8 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
                                                  _ptr(log[k]), st))
             _lib.check(lib.rlca_policy_backward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(policy.grad), st))
             if process_group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(policy.grad, group=process_group if process_group is not True else None)
+                from ..parallel import average_gradients
+                average_gradients(policy.grad, None if process_group is True else process_group)
             optimizer.step(grad_scale=1.0 / world)
             k += 1
     rows = log[:k].cpu().tolist()

@@ -1,0 +1,71 @@
+"""N>1 host logic on CPU with the gloo backend, world_size 2 (no GPU needed)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rl_collision_avoidance_b200.parallel import (allreduce_moments, average_gradients, broadcast_parameters,
+                                                 normalize_from_moments, shard_worlds)
+
+
+def test_shard_worlds_covers_everything_once():
+    for total, ws in ((171, 1), (171, 2), (171, 8), (328, 8), (7, 8)):
+        seen = []
+        for r in range(ws):
+            off, cnt = shard_worlds(total, r, ws)
+            seen += list(range(off, off + cnt))
+        assert seen == list(range(total))
+    with pytest.raises(ValueError):
+        shard_worlds(10, 3, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world_size, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    try:
+        rs = np.random.RandomState(0)
+        full = torch.from_numpy(rs.standard_normal(1000) * 2.0 + 0.5)
+        off, cnt = shard_worlds(10, rank, world_size)          # 10 "worlds" of 100 advantages each
+        local = full[off * 100:(off + cnt) * 100].float()
+        mom = torch.tensor([local.double().sum(), (local.double() ** 2).sum(), float(local.numel())], dtype=torch.float64)
+        allreduce_moments(mom)
+        norm = normalize_from_moments(local, mom)
+        ref = ((full - full.mean()) / full.std(unbiased=False))[off * 100:(off + cnt) * 100].float()
+        ok_norm = bool((norm - ref).abs().max() < 1e-6)
+        g = torch.full((16,), float(rank + 1))
+        average_gradients(g)
+        ok_grad = bool((g == 3.0).all())                       # 1 + 2, the 1/world_size goes into Adam's grad_scale
+        p = torch.full((8,), float(rank))
+        broadcast_parameters(p, src=0)
+        ok_bcast = bool((p == 0).all())
+        out.put((rank, ok_norm, ok_grad, ok_bcast))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_collectives():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] and r[3] for r in res), res
