@@ -109,19 +109,30 @@ def run_cpu(steps, warmup, budget_s, threads=None):
     import numpy as np
     from oracle import oracle as orc_mod
     from helpers import make_pair, random_actions
-    if threads:
-        orc_mod.set_threads(threads)
-    cores = orc_mod.num_threads()
-    # probe on the full workload to size the bounded sample
+    # torchrun exports OMP_NUM_THREADS=1, and a cgroup CPU quota can make "all logical CPUs" slower than fewer
+    # threads; so probe a few thread counts on the full workload and keep the fastest (the fair CPU arm).
     _, _, orc = make_pair('stage1', num_worlds=WORLDS_PER_GPU, beams=BEAMS, auto_reset=True, seed=0, gpu=False)
     orc.reset_world()
     orc.reset_pose()
     rng = np.random.default_rng(0)
     acts = [random_actions(rng, orc.N) for _ in range(8)]
-    orc.step(acts[0])
-    t0 = time.perf_counter()
-    orc.step(acts[1])
-    t_tick = time.perf_counter() - t0
+    ncpu = len(os.sched_getaffinity(0))
+    cands = [threads] if threads else sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 32), min(ncpu, 16)},
+                                             reverse=True)
+    best = None
+    for c in cands:
+        orc_mod.set_threads(c)
+        orc.step(acts[0])
+        dts = []
+        for j in range(3):
+            t0 = time.perf_counter()
+            orc.step(acts[1 + j])
+            dts.append(time.perf_counter() - t0)
+        dt = sorted(dts)[1]                      # median of 3: CPU-quota throttling makes single ticks noisy
+        if best is None or dt < best[0]:
+            best = (dt, c)
+    t_tick, cores = best
+    orc_mod.set_threads(cores)
     worlds = WORLDS_PER_GPU
     total = (steps + warmup) * t_tick
     if total > budget_s:

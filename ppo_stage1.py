@@ -99,6 +99,10 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
                   (s['update'], s['rollout_s'], s['update_s'], s['agent_steps_per_s'], s['mean_ep_reward']))
     except KeyboardInterrupt:
         pass
+    finally:
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':
