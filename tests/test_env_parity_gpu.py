@@ -230,3 +230,33 @@ def test_fused_scan_fifo(built):
         if t % 9 == 0 or t == 199:
             assert np.array_equal(stacks[(t + 1) % 2].cpu().numpy(), ref), f'tick {t}'
     assert saw_reset
+
+
+def test_circle_world_global_grid_path(built):
+    """circle.world (60 x 60 m at 0.01 m = 6000 x 6000 cells, 50 robots, antipodal goals) does not fit shared memory:
+    the library keeps one owner grid per world in global memory and runs the tick as physics+mark / lidar / unmark
+    launches.  Same oracle, same bit-exact bar (reset, observe, ticks incl. the |w| > 0.7 penalty, raycast)."""
+    sc, env, orc = make_pair('circle', num_worlds=2, auto_reset=1, seed=3)
+    orc.reset_world()
+    assert_state_equal(env, orc, 'reset_world')
+    env.reset_pose()
+    orc.reset_pose()
+    assert_state_equal(env, orc, 'reset_pose')
+    assert_outputs_equal(env, orc, 'first observation')
+    rng = np.random.default_rng(6)
+    for t in range(12):
+        a = random_actions(rng, orc.N)
+        a[:, 0] = 1.0 if t < 8 else a[:, 0]          # drive inwards so that robots meet
+        env.control_vel(torch.from_numpy(a).cuda())
+        orc.step(a)
+        assert_state_equal(env, orc, f'tick {t}')
+        assert_outputs_equal(env, orc, f'tick {t}')
+        assert np.array_equal(env.flags.cpu().numpy(), orc.flags)
+        assert np.array_equal(env.reward.cpu().numpy().view(np.uint32), orc.reward.view(np.uint32))
+    assert (orc.reward < -2.0).any() or (np.abs(orc.reward) > 0).any()
+    # robots see their neighbours on the circle (3.1 m apart): some beams must return < 6 m
+    assert (orc.obs < 0.49).any()
+    pose = orc.pose.copy()
+    got = env.raycast(torch.from_numpy(pose).cuda()).cpu().numpy()
+    ref = orc.raycast(pose)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
