@@ -202,6 +202,9 @@ int64_t rlca_policy_launch_count(const rlca_policy *pol);
 /* fc1 forward/backward GEMMs on the tcgen05 tensor cores with 3xTF32 error compensation (default on);
  * 0 selects the plain fp32 CUDA-core GEMM (kept as the cross-check for the tensor-core path). */
 int rlca_policy_set_tensor_cores(rlca_policy *pol, int32_t enable);
+/* Tell the workspace that params_dev changed (optimizer step, checkpoint load): derived copies of the weights
+ * (tf32 hi/lo splits, transposes) are rebuilt at the next forward.  A fresh workspace starts dirty. */
+int rlca_policy_weights_changed(rlca_policy *pol);
 
 /* Workspace sized for batches up to max_batch rows. */
 int rlca_policy_create(int32_t max_batch, rlca_policy **out);

@@ -92,6 +92,7 @@ struct rlca_policy {
     float *S;        // split-reduction scratch: [RSPLIT][2][max(CONV_PART, 128*260)]
     // ---- tensor-core (3xTF32) path for fc1: hi/lo splits of the operands, all K-major
     int use_tc;
+    int weights_dirty;   // W1 hi/lo/transposed copies must be rebuilt at the next forward
     int bpad;        // max_batch rounded up to 32 (row pitch of the transposed operands)
     float *Fs;       // [2 towers][hi,lo][B][4096]
     float *W1s;      // [2][hi,lo][256][4096]
@@ -179,7 +180,7 @@ __device__ __forceinline__ void conv1_tower(ConvSmem &sm, int t, int lt)
 }
 
 __global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__restrict__ obs, TowerPtrs ta, TowerPtrs tc,
-                                                             float *__restrict__ F, int nb)
+                                                             float *__restrict__ F, float *__restrict__ Fs, int nb)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smem_raw);
@@ -221,10 +222,22 @@ __global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__rest
         }
     }
     float *out = F + ((size_t)t * nb + n) * FEAT;
+    // optional tf32 hi/lo split of the features for the tensor-core fc1 (Fs = [tower][hi,lo][nb][4096])
+    float *out_hi = Fs ? Fs + ((size_t)(2 * t) * nb + n) * FEAT : nullptr;
+    float *out_lo = Fs ? Fs + ((size_t)(2 * t + 1) * nb + n) * FEAT : nullptr;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) out[(cg * 8 + c) * 128 + pg + 32 * i] = fmaxf(acc[i][c], 0.0f);
+        for (int i = 0; i < 4; ++i) {
+            const float v = fmaxf(acc[i][c], 0.0f);
+            const int o = (cg * 8 + c) * 128 + pg + 32 * i;
+            out[o] = v;
+            if (Fs) {
+                const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                out_hi[o] = h;
+                out_lo[o] = v - h;
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------ conv tower backward
@@ -925,6 +938,7 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
         int rc = rlca_tc_init();
         if (rc) return rc;
         p->use_tc = 1;
+        p->weights_dirty = 1;
     }
     RLCA_CUDA_TRY(cudaFuncSetAttribute(conv_tower_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ConvSmem)));
@@ -946,6 +960,13 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
 
 extern "C" int64_t rlca_policy_launch_count(const rlca_policy *p) { return p ? p->launches : -1; }
 
+extern "C" int rlca_policy_weights_changed(rlca_policy *p)
+{
+    if (!p) return rlca_set_err(RLCA_ERR_INVALID, "policy is NULL");
+    p->weights_dirty = 1;
+    return RLCA_OK;
+}
+
 extern "C" int rlca_policy_set_tensor_cores(rlca_policy *p, int32_t enable)
 {
     if (!p) return rlca_set_err(RLCA_ERR_INVALID, "policy is NULL");
@@ -960,7 +981,7 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
     if (nb < 1 || nb > pol->max_batch) return rlca_set_err(RLCA_ERR_INVALID, "nb exceeds the workspace max_batch");
     cudaStream_t s = (cudaStream_t)stream;
     const TowerPtrs ta = tower_ptrs(params, 0), tc = tower_ptrs(params, 1);
-    conv_tower_fwd_kernel<<<nb, 256, sizeof(ConvSmem), s>>>(obs, ta, tc, pol->F, nb);
+    conv_tower_fwd_kernel<<<nb, 256, sizeof(ConvSmem), s>>>(obs, ta, tc, pol->F, pol->use_tc ? pol->Fs : nullptr, nb);
     GemmArgs g{};
     if (pol->use_tc) {
         // fc1 on the tensor cores: split F and W1 into tf32 hi/lo parts, split-K 3xTF32 GEMM, fused bias+ReLU reduce
@@ -971,10 +992,11 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
             float *Fh = pol->Fs + (size_t)(2 * t) * B * FEAT, *Fl = Fh + B * FEAT;
             float *Wh = pol->W1s + (size_t)(2 * t) * WSZ, *Wl = Wh + WSZ;
             const float *w = t == 0 ? ta.fc1w : tc.fc1w;
-            rlca_tc_split(pol->F + (size_t)t * B * FEAT, nb, FEAT, FEAT, Fh, Fl, FEAT, s);
-            rlca_tc_split(w, 256, FEAT, FEAT, Wh, Wl, FEAT, s);
-            rlca_tc_transpose_split(w, 256, FEAT, FEAT, pol->W1Ts + (size_t)(2 * t) * WSZ, pol->W1Ts + (size_t)(2 * t + 1) * WSZ,
-                                    256, s);
+            if (pol->weights_dirty) {      // hi/lo (and transposed) copies of W1 are refreshed only after a weight change
+                rlca_tc_split(w, 256, FEAT, FEAT, Wh, Wl, FEAT, s);
+                rlca_tc_transpose_split(w, 256, FEAT, FEAT, pol->W1Ts + (size_t)(2 * t) * WSZ,
+                                        pol->W1Ts + (size_t)(2 * t + 1) * WSZ, 256, s);
+            }
             pr[t] = RlcaTcProblem{Fh, Fl, Wh, Wl, FEAT, FEAT, pol->P + (size_t)t * B * 256, nullptr};
         }
         const int mtiles = (nb + 127) / 128;
@@ -985,7 +1007,8 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
         if (rc) return rc;
         rlca_tc_splitk_bias_relu(pol->P, splits, split_stride, (long long)nb * 256, ta.fc1b, tc.fc1b, nb, 256, pol->X,
                                  pol->X + (size_t)nb * XLD, XLD, s);
-        pol->launches += 8;
+        pol->launches += pol->weights_dirty ? 6 : 2;
+        pol->weights_dirty = 0;
     } else {
         // fc1: X[:, :256] = relu(F W1^T + b1)
         g.M = nb; g.N = 256; g.K = FEAT; g.lda = FEAT; g.ldb = FEAT; g.ldc = XLD; g.relu = 1;

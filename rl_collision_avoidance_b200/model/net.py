@@ -86,6 +86,12 @@ class CNNPolicy:
             fan_in = math.prod(wshape[1:])
             bound = 1.0 / math.sqrt(fan_in)
             v.copy_(((torch.rand(shape, generator=gen) * 2 - 1) * bound).to(self.device))
+        self.weights_changed()
+
+    def weights_changed(self):
+        """Call after writing to the parameter buffer outside Adam.step / load_state_dict."""
+        if getattr(self, '_ws', None) is not None:
+            _lib.check(self.lib.rlca_policy_weights_changed(self._ws))
 
     def parameters(self):
         pl = ParamList(self.views.values())
@@ -106,6 +112,7 @@ class CNNPolicy:
         for k, v in self.views.items():
             if k in sd:
                 v.copy_(sd[k].to(device=self.device, dtype=torch.float32).view(v.shape))
+        self.weights_changed()
         return self
 
     def cuda(self):
@@ -213,6 +220,7 @@ class Adam:
         _lib.check(p.lib.rlca_adam_step(_ptr(p.flat), _ptr(p.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                         p.flat_size, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
                                         grad_scale, p._stream()))
+        p.weights_changed()
 
     def state_dict(self):
         return {'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(), 'step': self.step_count,
