@@ -89,6 +89,7 @@ struct rlca_policy {
     float *part;     // [2][B][CONV_PART]
     float *headpart; // [chunks][3][128 + 4]
     float *red;      // small reduction scratch (64 floats)
+    float *Wc;       // prepared conv weights [2][CONV_WBLK] (transposed for conflict-free staging)
     float *S;        // split-reduction scratch: [RSPLIT][2][max(CONV_PART, 128*260)]
     // ---- tensor-core (3xTF32) path for fc1: hi/lo splits of the operands, all K-major
     int use_tc;
@@ -108,43 +109,60 @@ struct rlca_policy {
 // One CTA per sample; threads 0..127 run the actor tower, 128..255 the critic tower.
 // conv1: Conv1d(3,32,k5,s2,p1) 512 -> 255 ; conv2: Conv1d(32,32,k3,s2,p1) 255 -> 128 (model/net.py:21-22,42-43).
 // h1 is kept in shared memory split into even/odd positions so conv2's stride-2 reads are conflict free:
-// stored index s = q+1 (q = -1..255, zeros at both ends); even s -> h1e[s/2], odd s -> h1o[s/2].
+// stored index s = q+1 (q = -1..255, zeros at both ends); even s -> h1e[s/2], odd s -> h1o[s/2].  The input scan is
+// split the same way (xe/xo) for conv1's stride-2 reads, and h1o is skewed by 16 floats so that the conv1 stores of
+// one warp (alternating even/odd s) spread over all 32 banks.
+// Weights come from a pre-transposed block Wc[tower] = w1t[15][32] | b1[32] | w2t[96][32] | b2[32] built by
+// conv_prep_weights_kernel, so staging them is a conflict-free linear copy (the in-kernel transpose used to cost
+// 39 % of this kernel's shared-memory wavefronts, profiles/README_r1.md).
+#define CONV_WBLK 3616          // floats per tower in the prepared weight block
+#define CONV_SPC 4              // samples per CTA: amortises the 29 KB weight staging
 struct ConvSmem {
-    float xs[3][520];            // xs[c][i+1] = x[c][i], zero padded
-    float w1[2][15][32];         // [tower][ci*5+k][co]
-    float b1[2][32];
-    float w2[2][96][32];         // [tower][ci*3+k][co]
-    float b2[2][32];
+    float wc[2][CONV_WBLK];      // [tower]: w1t | b1 | w2t | b2
+    float xe[3][264], xo[3][264];   // x de-interleaved: padded index j = i+1 (j = 0..513); even j -> xe[j/2], odd -> xo[j/2]
     float h1e[2][32][132];
+    float skew[16];
     float h1o[2][32][132];
 };
+#define WC_W1(sm, t, j) (&(sm).wc[t][(j) * 32])
+#define WC_B1(sm, t) (&(sm).wc[t][480])
+#define WC_W2(sm, t, j) (&(sm).wc[t][512 + (j) * 32])
+#define WC_B2(sm, t) (&(sm).wc[t][512 + 3072])
 
-__device__ __forceinline__ void conv_load_common(ConvSmem &sm, const float *__restrict__ obs_n, const TowerPtrs &ta,
-                                                 const TowerPtrs &tc, int tid, int nthreads)
+// Wc[t] from the state_dict layouts (co, ci, k): w1t[ci*5+k][co], w2t[ci*3+k][co]
+__global__ void conv_prep_weights_kernel(TowerPtrs ta, TowerPtrs tc, float *__restrict__ Wc)
 {
-    for (int i = tid; i < 3 * 520; i += nthreads) {
-        int c = i / 520, j = i - c * 520;
-        sm.xs[c][j] = (j >= 1 && j <= 512) ? obs_n[c * 512 + (j - 1)] : 0.0f;
-    }
-    for (int i = tid; i < 2 * 480; i += nthreads) {
-        int t = i / 480, r = i - t * 480;
-        int co = r / 15, j = r - co * 15;                 // weight layout (co, ci, k) row-major
-        sm.w1[t][j][co] = (t == 0 ? ta.cv1w : tc.cv1w)[r];
-    }
-    for (int i = tid; i < 2 * 3072; i += nthreads) {
-        int t = i / 3072, r = i - t * 3072;
-        int co = r / 96, j = r - co * 96;
-        sm.w2[t][j][co] = (t == 0 ? ta.cv2w : tc.cv2w)[r];
-    }
-    if (tid < 64) {
-        int t = tid >> 5, c = tid & 31;
-        sm.b1[t][c] = (t == 0 ? ta.cv1b : tc.cv1b)[c];
-        sm.b2[t][c] = (t == 0 ? ta.cv2b : tc.cv2b)[c];
-    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    if (i >= CONV_WBLK) return;
+    const TowerPtrs &tp = t == 0 ? ta : tc;
+    float v;
+    if (i < 480) { const int j = i >> 5, co = i & 31; v = tp.cv1w[co * 15 + j]; }
+    else if (i < 512) v = tp.cv1b[i - 480];
+    else if (i < 512 + 3072) { const int r = i - 512, j = r >> 5, co = r & 31; v = tp.cv2w[co * 96 + j]; }
+    else v = tp.cv2b[i - 3584];
+    Wc[(size_t)t * CONV_WBLK + i] = v;
+}
+
+__device__ __forceinline__ void conv_stage_weights(ConvSmem &sm, const float *__restrict__ Wc, int tid, int nthreads)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(Wc);
+    float4 *dst = reinterpret_cast<float4 *>(&sm.wc[0][0]);
+    for (int i = tid; i < 2 * CONV_WBLK / 4; i += nthreads) dst[i] = src[i];
     for (int i = tid; i < 2 * 32; i += nthreads) {
         int t = i >> 5, c = i & 31;
         sm.h1e[t][c][0] = 0.0f;        // s = 0   (q = -1)
         sm.h1e[t][c][128] = 0.0f;      // s = 256 (q = 255)
+    }
+}
+
+__device__ __forceinline__ void conv_stage_x(ConvSmem &sm, const float *__restrict__ obs_n, int tid, int nthreads)
+{
+    // padded index j = i + 1; j = 0 and j >= 513 are the zero padding of Conv1d(padding=1)
+    for (int i = tid; i < 3 * 264; i += nthreads) {
+        const int c = i / 264, h = i - c * 264;
+        const int je = 2 * h, jo = 2 * h + 1;
+        sm.xe[c][h] = (je >= 1 && je <= 512) ? obs_n[c * 512 + je - 1] : 0.0f;
+        sm.xo[c][h] = (jo >= 1 && jo <= 512) ? obs_n[c * 512 + jo - 1] : 0.0f;
     }
 }
 
@@ -157,17 +175,21 @@ __device__ __forceinline__ void conv1_tower(ConvSmem &sm, int t, int lt)
         if (p >= 255) break;
         float xv[15];
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-            for (int k = 0; k < 5; ++k) xv[ci * 5 + k] = sm.xs[ci][2 * p + k];   // input idx 2p+k-1, +1 offset
+        for (int ci = 0; ci < 3; ++ci) {          // padded input index 2p+k: k even -> xe[p + k/2], k odd -> xo[p + k/2]
+            xv[ci * 5 + 0] = sm.xe[ci][p];
+            xv[ci * 5 + 1] = sm.xo[ci][p];
+            xv[ci * 5 + 2] = sm.xe[ci][p + 1];
+            xv[ci * 5 + 3] = sm.xo[ci][p + 1];
+            xv[ci * 5 + 4] = sm.xe[ci][p + 2];
+        }
         const int s = p + 1;
         float *dst = (s & 1) ? &sm.h1o[t][0][s >> 1] : &sm.h1e[t][0][s >> 1];
 #pragma unroll
         for (int cg = 0; cg < 8; ++cg) {
-            float4 acc = *reinterpret_cast<const float4 *>(&sm.b1[t][cg * 4]);
+            float4 acc = *reinterpret_cast<const float4 *>(WC_B1(sm, t) + cg * 4);
 #pragma unroll
             for (int j = 0; j < 15; ++j) {
-                const float4 w = *reinterpret_cast<const float4 *>(&sm.w1[t][j][cg * 4]);
+                const float4 w = *reinterpret_cast<const float4 *>(WC_W1(sm, t, j) + cg * 4);
                 acc.x = fmaf(xv[j], w.x, acc.x); acc.y = fmaf(xv[j], w.y, acc.y);
                 acc.z = fmaf(xv[j], w.z, acc.z); acc.w = fmaf(xv[j], w.w, acc.w);
             }
@@ -179,205 +201,237 @@ __device__ __forceinline__ void conv1_tower(ConvSmem &sm, int t, int lt)
     }
 }
 
-__global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__restrict__ obs, TowerPtrs ta, TowerPtrs tc,
+__global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__restrict__ obs, const float *__restrict__ Wc,
                                                              float *__restrict__ F, float *__restrict__ Fs, int nb)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     ConvSmem &sm = *reinterpret_cast<ConvSmem *>(smem_raw);
-    const int n = blockIdx.x, tid = threadIdx.x;
-    conv_load_common(sm, obs + (size_t)n * 1536, ta, tc, tid, 256);
-    __syncthreads();
+    const int tid = threadIdx.x;
     const int t = tid >> 7, lt = tid & 127;
-    conv1_tower(sm, t, lt);
-    __syncthreads();
-    // conv2: thread = 4 positions (pg + 32 i) x 8 channels (cg*8 ..)
     const int pg = lt & 31, cg = lt >> 5;
-    float acc[4][8];
+    conv_stage_weights(sm, Wc, tid, 256);
+    for (int rep = 0; rep < CONV_SPC; ++rep) {
+        const int n = blockIdx.x * CONV_SPC + rep;
+        if (n >= nb) break;
+        if (rep) __syncthreads();                 // previous sample's conv2 has finished reading h1 / x
+        conv_stage_x(sm, obs + (size_t)n * 1536, tid, 256);
+        __syncthreads();
+        conv1_tower(sm, t, lt);
+        __syncthreads();
+        // conv2: thread = 4 positions (pg + 32 i) x 8 channels (cg*8 ..)
+        float acc[4][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[i][c] = sm.b2[t][cg * 8 + c];
+            for (int c = 0; c < 8; ++c) acc[i][c] = WC_B2(sm, t)[cg * 8 + c];
 #pragma unroll 2
-    for (int ci = 0; ci < 32; ++ci) {
-        float a0[4], a1[4], a2[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int p = pg + 32 * i;
-            a0[i] = sm.h1e[t][ci][p];        // k = 0: s = 2p
-            a1[i] = sm.h1o[t][ci][p];        // k = 1: s = 2p+1
-            a2[i] = sm.h1e[t][ci][p + 1];    // k = 2: s = 2p+2
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float4 wa = *reinterpret_cast<const float4 *>(&sm.w2[t][ci * 3 + k][cg * 8]);
-            const float4 wb = *reinterpret_cast<const float4 *>(&sm.w2[t][ci * 3 + k][cg * 8 + 4]);
+        for (int ci = 0; ci < 32; ++ci) {
+            float a0[4], a1[4], a2[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float a = k == 0 ? a0[i] : (k == 1 ? a1[i] : a2[i]);
-                acc[i][0] = fmaf(a, wa.x, acc[i][0]); acc[i][1] = fmaf(a, wa.y, acc[i][1]);
-                acc[i][2] = fmaf(a, wa.z, acc[i][2]); acc[i][3] = fmaf(a, wa.w, acc[i][3]);
-                acc[i][4] = fmaf(a, wb.x, acc[i][4]); acc[i][5] = fmaf(a, wb.y, acc[i][5]);
-                acc[i][6] = fmaf(a, wb.z, acc[i][6]); acc[i][7] = fmaf(a, wb.w, acc[i][7]);
+                const int p = pg + 32 * i;
+                a0[i] = sm.h1e[t][ci][p];        // k = 0: s = 2p
+                a1[i] = sm.h1o[t][ci][p];        // k = 1: s = 2p+1
+                a2[i] = sm.h1e[t][ci][p + 1];    // k = 2: s = 2p+2
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 wa = *reinterpret_cast<const float4 *>(WC_W2(sm, t, ci * 3 + k) + cg * 8);
+                const float4 wb = *reinterpret_cast<const float4 *>(WC_W2(sm, t, ci * 3 + k) + cg * 8 + 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float a = k == 0 ? a0[i] : (k == 1 ? a1[i] : a2[i]);
+                    acc[i][0] = fmaf(a, wa.x, acc[i][0]); acc[i][1] = fmaf(a, wa.y, acc[i][1]);
+                    acc[i][2] = fmaf(a, wa.z, acc[i][2]); acc[i][3] = fmaf(a, wa.w, acc[i][3]);
+                    acc[i][4] = fmaf(a, wb.x, acc[i][4]); acc[i][5] = fmaf(a, wb.y, acc[i][5]);
+                    acc[i][6] = fmaf(a, wb.z, acc[i][6]); acc[i][7] = fmaf(a, wb.w, acc[i][7]);
+                }
             }
         }
+        float *out = F + ((size_t)t * nb + n) * FEAT;
+        // optional tf32 hi/lo split of the features for the tensor-core fc1 (Fs = [tower][hi,lo][nb][4096])
+        float *out_hi = Fs ? Fs + ((size_t)(2 * t) * nb + n) * FEAT : nullptr;
+        float *out_lo = Fs ? Fs + ((size_t)(2 * t + 1) * nb + n) * FEAT : nullptr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = fmaxf(acc[i][c], 0.0f);
+                const int o = (cg * 8 + c) * 128 + pg + 32 * i;
+                out[o] = v;
+                if (Fs) {
+                    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                    out_hi[o] = h;
+                    out_lo[o] = v - h;
+                }
+            }
     }
-    float *out = F + ((size_t)t * nb + n) * FEAT;
-    // optional tf32 hi/lo split of the features for the tensor-core fc1 (Fs = [tower][hi,lo][nb][4096])
-    float *out_hi = Fs ? Fs + ((size_t)(2 * t) * nb + n) * FEAT : nullptr;
-    float *out_lo = Fs ? Fs + ((size_t)(2 * t + 1) * nb + n) * FEAT : nullptr;
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float v = fmaxf(acc[i][c], 0.0f);
-            const int o = (cg * 8 + c) * 128 + pg + 32 * i;
-            out[o] = v;
-            if (Fs) {
-                const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-                out_hi[o] = h;
-                out_lo[o] = v - h;
-            }
-        }
 }
 
 // ------------------------------------------------------------------------------------ conv tower backward
-// One CTA per (sample, tower), 256 threads.  dF (already masked by relu(conv2)) is d(conv2 pre-activation).
+// One CTA per (CONV_SPC samples, tower), 256 threads.  dF (already masked by relu(conv2)) is d(conv2 pre-activation).
+// Shared-memory layouts are chosen so that every hot loop reads conflict-free or by broadcast:
+//   g2t[p][co] / g1t[s][co]  position-major with pitch 33 (lanes over co: consecutive; lanes over p: stride 33)
+//   h1e / h1o                channel-major even/odd split as in the forward kernel (read by broadcast here)
+//   w2c[co][ci*3+k]          the state_dict layout (12 consecutive weights per (co, 4 ci) -> 3 broadcast LDS.128)
 struct ConvBwdSmem {
-    float xs[3][520];
-    float w1[15][32];
+    float w1[15][32];            // w1t from the prepared block
     float b1[32];
-    float w2[96][32];            // [ci*3+k][co]
-    float h1e[32][132], h1o[32][132];
-    float g2[32][128];           // d conv2 pre-activation [co][p]
-    float g1e[32][132], g1o[32][132];   // d conv1 pre-activation, same even/odd layout as h1 (s = q+1)
+    float w2c[32][96];
+    float xe[3][264], xo[3][264];
+    float h1e[32][132];
+    float skew[16];
+    float h1o[32][132];
+    float g2t[129][33];          // d conv2 pre-activation, row 128 = 0; reused as the dW1 reduction scratch
+    float g1t[257][33];          // d conv1 pre-activation at stored index s = q+1 (rows 0 and 256 unused)
 };
 
-__global__ void __launch_bounds__(256) conv_tower_bwd_kernel(const float *__restrict__ obs, TowerPtrs ta, TowerPtrs tc,
-                                                             const float *__restrict__ dF, float *__restrict__ part,
-                                                             int nb)
+__global__ void __launch_bounds__(256) conv_tower_bwd_kernel(const float *__restrict__ obs, const float *__restrict__ Wc,
+                                                             TowerPtrs ta, TowerPtrs tc, const float *__restrict__ dF,
+                                                             float *__restrict__ part, int nb)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     ConvBwdSmem &sm = *reinterpret_cast<ConvBwdSmem *>(smem_raw);
-    const int n = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+    const int t = blockIdx.y, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const TowerPtrs &tp = t == 0 ? ta : tc;
-    const float *obs_n = obs + (size_t)n * 1536;
-    for (int i = tid; i < 3 * 520; i += 256) {
-        int c = i / 520, j = i - c * 520;
-        sm.xs[c][j] = (j >= 1 && j <= 512) ? obs_n[c * 512 + (j - 1)] : 0.0f;
+    {   // weights: w1t | b1 from the prepared block, conv2 weights in their native (co, ci, k) order
+        const float4 *src = reinterpret_cast<const float4 *>(Wc + (size_t)t * CONV_WBLK);
+        float4 *dst = reinterpret_cast<float4 *>(&sm.w1[0][0]);
+        for (int i = tid; i < 512 / 4; i += 256) dst[i] = src[i];
+        const float4 *src2 = reinterpret_cast<const float4 *>(tp.cv2w);
+        float4 *dst2 = reinterpret_cast<float4 *>(&sm.w2c[0][0]);
+        for (int i = tid; i < 3072 / 4; i += 256) dst2[i] = src2[i];
+        if (tid < 32) { sm.h1e[tid][0] = 0.f; sm.h1e[tid][128] = 0.f; }
     }
-    for (int r = tid; r < 480; r += 256) { int co = r / 15, j = r - co * 15; sm.w1[j][co] = tp.cv1w[r]; }
-    for (int r = tid; r < 3072; r += 256) { int co = r / 96, j = r - co * 96; sm.w2[j][co] = tp.cv2w[r]; }
-    if (tid < 32) {
-        sm.b1[tid] = tp.cv1b[tid];
-        sm.h1e[tid][0] = 0.f; sm.h1e[tid][128] = 0.f;
-        sm.g1e[tid][0] = 0.f; sm.g1e[tid][128] = 0.f;
-    }
-    const float *dF_n = dF + ((size_t)t * nb + n) * FEAT;
-    for (int i = tid; i < 4096; i += 256) sm.g2[i >> 7][i & 127] = dF_n[i];
-    __syncthreads();
-    // recompute h1 = relu(conv1(x))  (256 threads: position tid, tid < 255)
-    if (tid < 255) {
-        const int p = tid;
-        float xv[15];
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-            for (int k = 0; k < 5; ++k) xv[ci * 5 + k] = sm.xs[ci][2 * p + k];
-        const int s = p + 1;
-        float *dst = (s & 1) ? &sm.h1o[0][s >> 1] : &sm.h1e[0][s >> 1];
-#pragma unroll
-        for (int cg = 0; cg < 8; ++cg) {
-            float4 acc = *reinterpret_cast<const float4 *>(&sm.b1[cg * 4]);
-#pragma unroll
-            for (int j = 0; j < 15; ++j) {
-                const float4 w = *reinterpret_cast<const float4 *>(&sm.w1[j][cg * 4]);
-                acc.x = fmaf(xv[j], w.x, acc.x); acc.y = fmaf(xv[j], w.y, acc.y);
-                acc.z = fmaf(xv[j], w.z, acc.z); acc.w = fmaf(xv[j], w.w, acc.w);
-            }
-            dst[(cg * 4 + 0) * 132] = fmaxf(acc.x, 0.0f);
-            dst[(cg * 4 + 1) * 132] = fmaxf(acc.y, 0.0f);
-            dst[(cg * 4 + 2) * 132] = fmaxf(acc.z, 0.0f);
-            dst[(cg * 4 + 3) * 132] = fmaxf(acc.w, 0.0f);
+    for (int rep = 0; rep < CONV_SPC; ++rep) {
+        const int n = blockIdx.x * CONV_SPC + rep;
+        if (n >= nb) break;
+        __syncthreads();
+        const float *obs_n = obs + (size_t)n * 1536;
+        for (int i = tid; i < 3 * 264; i += 256) {
+            const int c = i / 264, h = i - c * 264;
+            const int je = 2 * h, jo = 2 * h + 1;
+            sm.xe[c][h] = (je >= 1 && je <= 512) ? obs_n[c * 512 + je - 1] : 0.0f;
+            sm.xo[c][h] = (jo >= 1 && jo <= 512) ? obs_n[c * 512 + jo - 1] : 0.0f;
         }
-    }
-    __syncthreads();
-    float *out = part + ((size_t)t * nb + n) * CONV_PART;
-    // (a) dW2[co][ci][k] = sum_p g2[co][p] * h1[ci][2p+k-1]; thread: co = tid>>3, ci = (tid&7)*4 .. +3
-    {
-        const int co = tid >> 3, ci0 = (tid & 7) * 4;
-        float acc[4][3];
+        const float *dF_n = dF + ((size_t)t * nb + n) * FEAT;
+        for (int i = tid; i < 4096; i += 256) sm.g2t[i & 127][i >> 7] = dF_n[i];     // coalesced read, stride-33 write
+        if (tid < 33) sm.g2t[128][tid] = 0.0f;
+        __syncthreads();
+        // ---- recompute h1 = relu(conv1(x)): thread = position (255 of them)
+        if (tid < 255) {
+            const int p = tid;
+            float xv[15];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = 0.0f;
-        for (int p = 0; p < 128; p += 4) {
-            const float4 g = *reinterpret_cast<const float4 *>(&sm.g2[co][p]);
+            for (int ci = 0; ci < 3; ++ci) {
+                xv[ci * 5 + 0] = sm.xe[ci][p];     xv[ci * 5 + 1] = sm.xo[ci][p];
+                xv[ci * 5 + 2] = sm.xe[ci][p + 1]; xv[ci * 5 + 3] = sm.xo[ci][p + 1];
+                xv[ci * 5 + 4] = sm.xe[ci][p + 2];
+            }
+            const int s = p + 1;
+            float *dst = (s & 1) ? &sm.h1o[0][s >> 1] : &sm.h1e[0][s >> 1];
+#pragma unroll
+            for (int cg = 0; cg < 8; ++cg) {
+                float4 acc = *reinterpret_cast<const float4 *>(&sm.b1[cg * 4]);
+#pragma unroll
+                for (int j = 0; j < 15; ++j) {
+                    const float4 w = *reinterpret_cast<const float4 *>(&sm.w1[j][cg * 4]);
+                    acc.x = fmaf(xv[j], w.x, acc.x); acc.y = fmaf(xv[j], w.y, acc.y);
+                    acc.z = fmaf(xv[j], w.z, acc.z); acc.w = fmaf(xv[j], w.w, acc.w);
+                }
+                dst[(cg * 4 + 0) * 132] = fmaxf(acc.x, 0.0f);
+                dst[(cg * 4 + 1) * 132] = fmaxf(acc.y, 0.0f);
+                dst[(cg * 4 + 2) * 132] = fmaxf(acc.z, 0.0f);
+                dst[(cg * 4 + 3) * 132] = fmaxf(acc.w, 0.0f);
+            }
+        }
+        __syncthreads();
+        float *out = part + ((size_t)t * nb + n) * CONV_PART;
+        // ---- (a) dW2[co][ci][k] = sum_p g2[co][p] h1[ci][2p+k-1]: lane = co, warp = 4 input channels
+        {
+            const int co = lane, ci0 = warp * 4;
+            float acc[4][3];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[a][0] = acc[a][1] = acc[a][2] = 0.0f;
+            float bsum = 0.0f;
+            for (int p = 0; p < 128; p += 4) {
+                const float g0 = sm.g2t[p][co], g1v = sm.g2t[p + 1][co], g2v = sm.g2t[p + 2][co], g3 = sm.g2t[p + 3][co];
+                bsum += (g0 + g1v) + (g2v + g3);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const float4 e = *reinterpret_cast<const float4 *>(&sm.h1e[ci0 + a][p]);     // broadcast
+                    const float e4 = sm.h1e[ci0 + a][p + 4];
+                    const float4 o = *reinterpret_cast<const float4 *>(&sm.h1o[ci0 + a][p]);
+                    acc[a][0] = fmaf(g0, e.x, fmaf(g1v, e.y, fmaf(g2v, e.z, fmaf(g3, e.w, acc[a][0]))));
+                    acc[a][1] = fmaf(g0, o.x, fmaf(g1v, o.y, fmaf(g2v, o.z, fmaf(g3, o.w, acc[a][1]))));
+                    acc[a][2] = fmaf(g0, e.y, fmaf(g1v, e.z, fmaf(g2v, e.w, fmaf(g3, e4, acc[a][2]))));
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) out[co * 96 + (ci0 + a) * 3 + k] = acc[a][k];
+            if (warp == 0) out[3072 + co] = bsum;                     // (b) db2[co] = sum_p g2[co][p]
+        }
+        // ---- (c) dh1[ci][q] = sum_co sum_k g2[co][p] w2[co][ci][k], q = 2p+k-1, masked by h1 > 0
+        //      item = (m = 0..127, 4 input channels): q = 2m (k=1, p=m) and q = 2m+1 (k=0, p=m+1 ; k=2, p=m)
+        for (int wi = tid; wi < 128 * 8; wi += 256) {
+            const int m = wi & 127, ci0 = (wi >> 7) * 4;
+            float ev[4] = {0.f, 0.f, 0.f, 0.f}, od[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+            for (int co = 0; co < 32; ++co) {
+                const float gm = sm.g2t[m][co], gm1 = sm.g2t[m + 1][co];      // row 128 is zero
+                const float4 wa = *reinterpret_cast<const float4 *>(&sm.w2c[co][ci0 * 3]);       // broadcast
+                const float4 wb = *reinterpret_cast<const float4 *>(&sm.w2c[co][ci0 * 3 + 4]);
+                const float4 wc = *reinterpret_cast<const float4 *>(&sm.w2c[co][ci0 * 3 + 8]);
+                const float w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    ev[a] = fmaf(gm, w[a * 3 + 1], ev[a]);
+                    od[a] = fmaf(gm1, w[a * 3 + 0], fmaf(gm, w[a * 3 + 2], od[a]));
+                }
+            }
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const float4 e = *reinterpret_cast<const float4 *>(&sm.h1e[ci0 + a][p]);
-                const float e4 = sm.h1e[ci0 + a][p + 4];
-                const float4 o = *reinterpret_cast<const float4 *>(&sm.h1o[ci0 + a][p]);
-                acc[a][0] = fmaf(g.x, e.x, fmaf(g.y, e.y, fmaf(g.z, e.z, fmaf(g.w, e.w, acc[a][0]))));
-                acc[a][1] = fmaf(g.x, o.x, fmaf(g.y, o.y, fmaf(g.z, o.z, fmaf(g.w, o.w, acc[a][1]))));
-                acc[a][2] = fmaf(g.x, e.y, fmaf(g.y, e.z, fmaf(g.z, e.w, fmaf(g.w, e4, acc[a][2]))));
+                // q = 2m -> s = 2m+1 ; q = 2m+1 -> s = 2m+2 (q = 255 does not exist)
+                sm.g1t[2 * m + 1][ci0 + a] = sm.h1o[ci0 + a][m] > 0.0f ? ev[a] : 0.0f;
+                if (m < 127) sm.g1t[2 * m + 2][ci0 + a] = sm.h1e[ci0 + a][m + 1] > 0.0f ? od[a] : 0.0f;
             }
         }
+        __syncthreads();
+        // ---- (d) dW1[co][ci][k] = sum_p g1[co][p] x[ci][2p+k-1], db1[co] = sum_p g1[co][p]  (p = 0..254, s = p+1):
+        //      lane = co, warp w takes positions p = w, w+8, ...; 16 partial sums per thread, reduced across warps
+        {
+            const int co = lane;
+            float acc[16];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+            for (int p = warp; p < 255; p += 8) {
+                const float g = sm.g1t[p + 1][co];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) out[co * 96 + (ci0 + a) * 3 + k] = acc[a][k];
-    }
-    // (b) db2[co] = sum_p g2[co][p]  (one warp-row each: 32 threads x 4 values, shuffle reduce)
-    {
-        const int w = tid >> 5, lane = tid & 31;
-        for (int co = w; co < 32; co += 8) {
-            const float4 g = *reinterpret_cast<const float4 *>(&sm.g2[co][lane * 4]);
-            float sacc = (g.x + g.y) + (g.z + g.w);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-            if (lane == 0) out[3072 + co] = sacc;
-        }
-    }
-    // (c) dh1[ci][q] = sum_co sum_k g2[co][p] w2[co][ci][k], q = 2p+k-1, masked by h1 > 0.
-    //     work item = (m = 0..127, ci group of 4): q = 2m (k=1,p=m) and q = 2m+1 (k=0,p=m+1 ; k=2,p=m)
-    for (int wi = tid; wi < 128 * 8; wi += 256) {
-        const int m = wi & 127, ci0 = (wi >> 7) * 4;
-        float ev[4] = {0.f, 0.f, 0.f, 0.f}, od[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int co = 0; co < 32; ++co) {
-            const float gm = sm.g2[co][m];
-            const float gm1 = m < 127 ? sm.g2[co][m + 1] : 0.0f;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const float w0 = sm.w2[(ci0 + a) * 3 + 0][co], w1v = sm.w2[(ci0 + a) * 3 + 1][co],
-                            w2v = sm.w2[(ci0 + a) * 3 + 2][co];
-                ev[a] = fmaf(gm, w1v, ev[a]);
-                od[a] = fmaf(gm1, w0, fmaf(gm, w2v, od[a]));
+                for (int ci = 0; ci < 3; ++ci) {
+                    acc[ci * 5 + 0] = fmaf(g, sm.xe[ci][p], acc[ci * 5 + 0]);
+                    acc[ci * 5 + 1] = fmaf(g, sm.xo[ci][p], acc[ci * 5 + 1]);
+                    acc[ci * 5 + 2] = fmaf(g, sm.xe[ci][p + 1], acc[ci * 5 + 2]);
+                    acc[ci * 5 + 3] = fmaf(g, sm.xo[ci][p + 1], acc[ci * 5 + 3]);
+                    acc[ci * 5 + 4] = fmaf(g, sm.xe[ci][p + 2], acc[ci * 5 + 4]);
+                }
+                acc[15] += g;
             }
-        }
+            float *red = &sm.g2t[0][0];                 // g2t is dead after (c): [warp][16][32] = 4096 floats <= 129*33
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            // q = 2m -> s = 2m+1 (odd, index m) ; q = 2m+1 -> s = 2m+2 (even, index m+1); q = 255 does not exist
-            sm.g1o[ci0 + a][m] = sm.h1o[ci0 + a][m] > 0.0f ? ev[a] : 0.0f;
-            if (m < 127) sm.g1e[ci0 + a][m + 1] = sm.h1e[ci0 + a][m + 1] > 0.0f ? od[a] : 0.0f;
+            for (int j = 0; j < 16; ++j) red[(warp * 16 + j) * 32 + co] = acc[j];
         }
-    }
-    __syncthreads();
-    // (d) dW1[co][ci][k] = sum_p g1[co][p] * x[ci][2p+k-1] ; db1[co] = sum_p g1[co][p]   (p = 0..254, s = p+1)
-    for (int o = tid; o < 480 + 32; o += 256) {
-        float acc = 0.0f;
-        if (o < 480) {
-            const int co = o / 15, j = o - co * 15, ci = j / 5, k = j - ci * 5;
-            for (int p = 0; p < 255; ++p) {
-                const int s = p + 1;
-                const float g = (s & 1) ? sm.g1o[co][s >> 1] : sm.g1e[co][s >> 1];
-                acc = fmaf(g, sm.xs[ci][2 * p + k], acc);
-            }
-            out[3104 + o] = acc;
-        } else {
-            const int co = o - 480;
-            for (int p = 0; p < 255; ++p) {
-                const int s = p + 1;
-                acc += (s & 1) ? sm.g1o[co][s >> 1] : sm.g1e[co][s >> 1];
-            }
-            out[3104 + 480 + co] = acc;
+        __syncthreads();
+        for (int o = tid; o < 512; o += 256) {
+            const int j = o >> 5, co = o & 31;
+            const float *red = &sm.g2t[0][0];
+            float v = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += red[(w * 16 + j) * 32 + co];
+            if (j < 15) out[3104 + co * 15 + j] = v;
+            else out[3104 + 480 + co] = v;
         }
     }
 }
@@ -924,6 +978,7 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
     RLCA_CUDA_TRY(cudaMalloc(&p->part, 2 * B * CONV_PART * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->headpart, (size_t)chunks * 3 * 132 * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->red, 64 * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->Wc, 2 * CONV_WBLK * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->S, (size_t)RSPLIT * 2 * 128 * XLD * sizeof(float)));
     p->bpad = (max_batch + 31) / 32 * 32;
     {
@@ -952,7 +1007,7 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
 {
     if (!p) return RLCA_OK;
     cudaFree(p->F); cudaFree(p->X); cudaFree(p->H2); cudaFree(p->dOut); cudaFree(p->dZ2); cudaFree(p->dX);
-    cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red); cudaFree(p->S);
+    cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red); cudaFree(p->S); cudaFree(p->Wc);
     cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P);
     delete p;
     return RLCA_OK;
@@ -971,6 +1026,7 @@ extern "C" int rlca_policy_set_tensor_cores(rlca_policy *p, int32_t enable)
 {
     if (!p) return rlca_set_err(RLCA_ERR_INVALID, "policy is NULL");
     p->use_tc = enable ? 1 : 0;
+    p->weights_dirty = 1;
     return RLCA_OK;
 }
 
@@ -981,7 +1037,9 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
     if (nb < 1 || nb > pol->max_batch) return rlca_set_err(RLCA_ERR_INVALID, "nb exceeds the workspace max_batch");
     cudaStream_t s = (cudaStream_t)stream;
     const TowerPtrs ta = tower_ptrs(params, 0), tc = tower_ptrs(params, 1);
-    conv_tower_fwd_kernel<<<nb, 256, sizeof(ConvSmem), s>>>(obs, ta, tc, pol->F, pol->use_tc ? pol->Fs : nullptr, nb);
+    if (pol->weights_dirty) conv_prep_weights_kernel<<<dim3((CONV_WBLK + 255) / 256, 2), 256, 0, s>>>(ta, tc, pol->Wc);
+    conv_tower_fwd_kernel<<<(nb + CONV_SPC - 1) / CONV_SPC, 256, sizeof(ConvSmem), s>>>(obs, pol->Wc, pol->F,
+                                                                                     pol->use_tc ? pol->Fs : nullptr, nb);
     GemmArgs g{};
     if (pol->use_tc) {
         // fc1 on the tensor cores: split F and W1 into tf32 hi/lo parts, split-K 3xTF32 GEMM, fused bias+ReLU reduce
@@ -1008,7 +1066,6 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
         rlca_tc_splitk_bias_relu(pol->P, splits, split_stride, (long long)nb * 256, ta.fc1b, tc.fc1b, nb, 256, pol->X,
                                  pol->X + (size_t)nb * XLD, XLD, s);
         pol->launches += pol->weights_dirty ? 6 : 2;
-        pol->weights_dirty = 0;
     } else {
         // fc1: X[:, :256] = relu(F W1^T + b1)
         g.M = nb; g.N = 256; g.K = FEAT; g.lda = FEAT; g.ldb = FEAT; g.ldc = XLD; g.relu = 1;
@@ -1026,6 +1083,7 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
         pol->H2, params + tensor_offset(T_A1W), params + tensor_offset(T_A1B), params + tensor_offset(T_A2W),
         params + tensor_offset(T_A2B), params + tensor_offset(T_CRITW), params + tensor_offset(T_CRITB), nb, value, mean);
     pol->launches += 5;
+    pol->weights_dirty = 0;
     RLCA_CUDA_TRY(cudaGetLastError());
     return RLCA_OK;
 }
@@ -1138,7 +1196,8 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     g.pr[1] = GemmProblem{pol->dX + B * XLD, tc.fc1w, nullptr, pol->F + B * FEAT, pol->dF + B * FEAT};
     launch_gemm<false, false>(g, 2, s);
     }
-    conv_tower_bwd_kernel<<<dim3(nb, 2), 256, sizeof(ConvBwdSmem), s>>>(obs, ta, tc, pol->dF, pol->part, nb);
+    conv_tower_bwd_kernel<<<dim3((nb + CONV_SPC - 1) / CONV_SPC, 2), 256, sizeof(ConvBwdSmem), s>>>(obs, pol->Wc, ta, tc, pol->dF,
+                                                                                                 pol->part, nb);
     conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(pol->part, nb, pol->S);
     conv_part_final_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->S, RSPLIT, ga, gc);
     pol->launches += 10;
