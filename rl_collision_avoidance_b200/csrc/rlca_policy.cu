@@ -838,23 +838,55 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
     p[i] -= (lr / bc1) * (mi / denom);
 }
 
-__global__ void gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
-                           const float *__restrict__ last_value, const uint8_t *__restrict__ dones, int T, int N,
-                           double gamma, double lam, float *__restrict__ targets, float *__restrict__ advs)
+// GAE as a blocked segmented scan over time (generate_train_data, model/ppo.py:122-139).
+// The recurrence A_t = delta_t + k_t A_{t+1} (k_t = gamma*lam*(1-d_t); a done flag cuts the segment) is affine, so a
+// chunk of GAE_CHUNK steps composes to A_first = P + Q * A_after.  Block = 8 time chunks x 32 agents:
+//   pass 1: every (chunk, agent) thread folds its chunk into (P, Q);        [parallel over T/GAE_CHUNK chunks]
+//   pass 2: the carry entering each chunk is folded from the later chunks in shared memory;
+//   pass 3: every thread replays its chunk from the carry and writes targets / advantages.
+// float64 like the reference's numpy; inputs are time-major (T, N) so a warp reads 32 consecutive agents (coalesced).
+#define GAE_CHUNKS 8
+__global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rewards, const float *__restrict__ values,
+                                                  const float *__restrict__ last_value, const uint8_t *__restrict__ dones,
+                                                  int T, int N, double gamma, double lam, float *__restrict__ targets,
+                                                  float *__restrict__ advs)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    double gae = 0.0, vnext = (double)last_value[i];
-    for (int t = T - 1; t >= 0; --t) {
-        const size_t k = (size_t)t * N + i;
-        const double nd = dones[k] ? 0.0 : 1.0;
-        const double v = (double)values[k];
-        const double delta = (double)rewards[k] + gamma * vnext * nd - v;
-        gae = delta + gamma * lam * nd * gae;
-        const double tgt = gae + v;
-        targets[k] = (float)tgt;
-        advs[k] = (float)(tgt - v);
-        vnext = v;
+    __shared__ double sP[GAE_CHUNKS][32], sQ[GAE_CHUNKS][32];
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int clen = (T + GAE_CHUNKS - 1) / GAE_CHUNKS;
+    const int t0 = c * clen, t1 = min(T, t0 + clen);            // this thread's time range [t0, t1)
+    const bool act = i < N;
+    double P = 0.0, Q = 1.0;
+    if (act) {
+        for (int t = t1 - 1; t >= t0; --t) {
+            const size_t k = (size_t)t * N + i;
+            const double nd = dones[k] ? 0.0 : 1.0;
+            const double vnext = (t + 1 < T) ? (double)values[k + N] : (double)last_value[i];
+            const double delta = (double)rewards[k] + gamma * vnext * nd - (double)values[k];
+            const double kk = gamma * lam * nd;
+            // A_t = delta + kk * (P + Q * A_after)
+            P = delta + kk * P;
+            Q = kk * Q;
+        }
+    }
+    sP[c][lane] = P; sQ[c][lane] = Q;
+    __syncthreads();
+    double carry = 0.0;                                          // A just after this chunk
+    for (int cc = GAE_CHUNKS - 1; cc > c; --cc) carry = sP[cc][lane] + sQ[cc][lane] * carry;
+    if (act) {
+        double gae = carry;
+        for (int t = t1 - 1; t >= t0; --t) {
+            const size_t k = (size_t)t * N + i;
+            const double nd = dones[k] ? 0.0 : 1.0;
+            const double v = (double)values[k];
+            const double vnext = (t + 1 < T) ? (double)values[k + N] : (double)last_value[i];
+            const double delta = (double)rewards[k] + gamma * vnext * nd - v;
+            gae = delta + gamma * lam * nd * gae;
+            const double tgt = gae + v;
+            targets[k] = (float)tgt;
+            advs[k] = (float)(tgt - v);
+        }
     }
 }
 
@@ -1223,7 +1255,7 @@ extern "C" int rlca_gae(const float *rewards, const float *values, const float *
 {
     if (!rewards || !values || !last_value || !dones || !targets || !advs || T < 1 || N < 1)
         return rlca_set_err(RLCA_ERR_INVALID, "bad GAE arguments");
-    gae_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, values, last_value, dones, T, N, (double)gamma,
+    gae_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(rewards, values, last_value, dones, T, N, (double)gamma,
                                                                (double)lam, targets, advs);
     RLCA_CUDA_TRY(cudaGetLastError());
     return RLCA_OK;
