@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__rest
         __syncthreads();
         conv1_tower(sm, t, lt);
         __syncthreads();
-        // conv2: thread = 4 positions (pg + 32 i) x 8 channels (cg*8 ..)
+        // conv2: thread = 4 consecutive positions (4 pg .. 4 pg + 3) x 8 channels (cg*8 ..): the three taps of the four
+        // positions need h1e[4pg .. 4pg+4] and h1o[4pg .. 4pg+3] -> two LDS.128 + one LDS.32 per input channel
         float acc[4][8];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -226,14 +227,12 @@ __global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__rest
             for (int c = 0; c < 8; ++c) acc[i][c] = WC_B2(sm, t)[cg * 8 + c];
 #pragma unroll 2
         for (int ci = 0; ci < 32; ++ci) {
-            float a0[4], a1[4], a2[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int p = pg + 32 * i;
-                a0[i] = sm.h1e[t][ci][p];        // k = 0: s = 2p
-                a1[i] = sm.h1o[t][ci][p];        // k = 1: s = 2p+1
-                a2[i] = sm.h1e[t][ci][p + 1];    // k = 2: s = 2p+2
-            }
+            const float4 e = *reinterpret_cast<const float4 *>(&sm.h1e[t][ci][4 * pg]);
+            const float e4 = sm.h1e[t][ci][4 * pg + 4];
+            const float4 o = *reinterpret_cast<const float4 *>(&sm.h1o[t][ci][4 * pg]);
+            const float a0[4] = {e.x, e.y, e.z, e.w};          // k = 0: s = 2p
+            const float a1[4] = {o.x, o.y, o.z, o.w};          // k = 1: s = 2p+1
+            const float a2[4] = {e.y, e.z, e.w, e4};           // k = 2: s = 2p+2
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const float4 wa = *reinterpret_cast<const float4 *>(WC_W2(sm, t, ci * 3 + k) + cg * 8);
@@ -253,18 +252,19 @@ __global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__rest
         float *out_hi = Fs ? Fs + ((size_t)(2 * t) * nb + n) * FEAT : nullptr;
         float *out_lo = Fs ? Fs + ((size_t)(2 * t + 1) * nb + n) * FEAT : nullptr;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float v = fmaxf(acc[i][c], 0.0f);
-                const int o = (cg * 8 + c) * 128 + pg + 32 * i;
-                out[o] = v;
-                if (Fs) {
-                    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-                    out_hi[o] = h;
-                    out_lo[o] = v - h;
-                }
+        for (int c = 0; c < 8; ++c) {
+            const int o = (cg * 8 + c) * 128 + 4 * pg;
+            const float4 v = make_float4(fmaxf(acc[0][c], 0.0f), fmaxf(acc[1][c], 0.0f), fmaxf(acc[2][c], 0.0f),
+                                         fmaxf(acc[3][c], 0.0f));
+            *reinterpret_cast<float4 *>(out + o) = v;
+            if (Fs) {
+                float4 h;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                *reinterpret_cast<float4 *>(out_hi + o) = h;
+                *reinterpret_cast<float4 *>(out_lo + o) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
+        }
     }
 }
 
@@ -376,27 +376,40 @@ __global__ void __launch_bounds__(256) conv_tower_bwd_kernel(const float *__rest
         }
         // ---- (c) dh1[ci][q] = sum_co sum_k g2[co][p] w2[co][ci][k], q = 2p+k-1, masked by h1 > 0
         //      item = (m = 0..127, 4 input channels): q = 2m (k=1, p=m) and q = 2m+1 (k=0, p=m+1 ; k=2, p=m)
-        for (int wi = tid; wi < 128 * 8; wi += 256) {
-            const int m = wi & 127, ci0 = (wi >> 7) * 4;
-            float ev[4] = {0.f, 0.f, 0.f, 0.f}, od[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+        {   // thread = (positions lane + 32 j, j = 0..3 ; 4 input channels): 8 conflict-free g loads (pitch 33) + 3 broadcast
+            // weight LDS.128 per co for 48 FMAs
+            const int ml = tid & 31, ci0 = (tid >> 5) * 4;
+            float ev[4][4], od[4][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int a = 0; a < 4; ++a) ev[j][a] = od[j][a] = 0.0f;
+#pragma unroll 2
             for (int co = 0; co < 32; ++co) {
-                const float gm = sm.g2t[m][co], gm1 = sm.g2t[m + 1][co];      // row 128 is zero
+                float g[4], gn[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { g[j] = sm.g2t[ml + 32 * j][co]; gn[j] = sm.g2t[ml + 32 * j + 1][co]; }   // row 128 is zero
                 const float4 wa = *reinterpret_cast<const float4 *>(&sm.w2c[co][ci0 * 3]);       // broadcast
                 const float4 wb = *reinterpret_cast<const float4 *>(&sm.w2c[co][ci0 * 3 + 4]);
                 const float4 wc = *reinterpret_cast<const float4 *>(&sm.w2c[co][ci0 * 3 + 8]);
                 const float w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    ev[a] = fmaf(gm, w[a * 3 + 1], ev[a]);
-                    od[a] = fmaf(gm1, w[a * 3 + 0], fmaf(gm, w[a * 3 + 2], od[a]));
-                }
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        ev[j][a] = fmaf(g[j], w[a * 3 + 1], ev[j][a]);
+                        od[j][a] = fmaf(gn[j], w[a * 3 + 0], fmaf(g[j], w[a * 3 + 2], od[j][a]));
+                    }
             }
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                // q = 2m -> s = 2m+1 ; q = 2m+1 -> s = 2m+2 (q = 255 does not exist)
-                sm.g1t[2 * m + 1][ci0 + a] = sm.h1o[ci0 + a][m] > 0.0f ? ev[a] : 0.0f;
-                if (m < 127) sm.g1t[2 * m + 2][ci0 + a] = sm.h1e[ci0 + a][m + 1] > 0.0f ? od[a] : 0.0f;
+            for (int j = 0; j < 4; ++j) {
+                const int m = ml + 32 * j;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    // q = 2m -> s = 2m+1 ; q = 2m+1 -> s = 2m+2 (q = 255 does not exist)
+                    sm.g1t[2 * m + 1][ci0 + a] = sm.h1o[ci0 + a][m] > 0.0f ? ev[j][a] : 0.0f;
+                    if (m < 127) sm.g1t[2 * m + 2][ci0 + a] = sm.h1e[ci0 + a][m + 1] > 0.0f ? od[j][a] : 0.0f;
+                }
             }
         }
         __syncthreads();
