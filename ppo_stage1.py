@@ -57,6 +57,8 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
     ap.add_argument('--updates', type=int, default=None, help='stop after this many PPO updates')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--policy-path', default='policy')
+    ap.add_argument('--scenario', default=None, choices=[None, 'stage1', 'stage2', 'circle'],
+                    help='override the world (e.g. circle: BASELINE config 4 trains on circle.world)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world_size = int(os.environ.get('WORLD_SIZE', '1'))
@@ -69,6 +71,9 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
         pg = True
     logger, logger_cal = make_loggers() if rank == 0 else (None, None)
     device = 'cuda:%d' % local_rank
+    if args.scenario == 'circle':
+        from rl_collision_avoidance_b200.circle_world import StageWorld as world_cls   # noqa: N813
+        num_env = 50
     env = world_cls(LASER_BEAM, index=0, num_env=num_env, num_worlds=args.num_worlds, device=device, seed=args.seed,
                     auto_reset=1 if stage == 1 else 2, world_offset=rank * args.num_worlds)
     action_bound = [[0, -1], [1, 1]]
