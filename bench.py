@@ -262,6 +262,19 @@ def main():
     if world_size > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = N * world_size * args.e2e_steps / float(te.item())
+    # variant for callers that keep the policy on the device: same call, but the observations stay in HBM
+    # (action H2D + tick + reward/flags/goal-speed D2H + sync).  Reported next to `e2e`, never instead of it.
+    for i in range(5):
+        env.step_host(a_host[i % 8], want_obs=False)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(args.e2e_steps):
+        env.step_host(a_host[i % 8], want_obs=False)
+    torch.cuda.synchronize(dev)
+    tn = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+    e2e_noobs = N * world_size * args.e2e_steps / float(tn.item())
 
     if rank == 0:
         value = N * world_size * args.steps / (ms_max * 1e-3)
@@ -293,6 +306,9 @@ def main():
                          'note': 'per-GPU; the march is issue/shared-memory bound, not HBM bound (DESIGN.md §6)'},
             'e2e': {'value': e2e_val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': N * 8 * world_size,
                     'd2h_bytes_per_step': N * (4 * BEAMS + 4 + 4 + 16) * world_size, 'steps': args.e2e_steps},
+            'e2e_obs_on_device': {'value': e2e_noobs, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': N * 8 * world_size,
+                                  'd2h_bytes_per_step': N * (4 + 4 + 16) * world_size,
+                                  'note': 'same host-buffer call with the scans left in HBM for an on-device policy'},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
