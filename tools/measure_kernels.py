@@ -70,6 +70,22 @@ def main():
                     'alg_bytes': by, 'GBps': by / t / 1e9, 'frac_of_measured_hbm': by / t / 1e9 / PEAK})
         env.close()
         del env, ring
+    # ---- fused tick on the other scenarios (stage 2: 200 x 200 map + polygons, group-synchronous; circle: global-grid path)
+    for scen, worlds, ar in (('stage2', 94, 2), ('circle', 41, 1)):
+        env = StageWorld(512, scenario=scen, num_worlds=worlds, seed=0, auto_reset=ar)
+        env.reset_pose()
+        acts = [torch.rand(env.N, 2, device='cuda') for _ in range(16)]
+        k = [0]
+
+        def g():
+            env.control_vel(acts[k[0] % 16])
+            k[0] += 1
+        t = timeit(g, n=100, warm=10)
+        by = env.N * (4 * 512 + 96)
+        out.append({'kernel': 'fused tick ' + scen, 'robots': env.N, 'beams': 512, 'us': t * 1e6, 'agent_steps_per_s': env.N / t,
+                    'alg_bytes': by, 'GBps': by / t / 1e9, 'frac_of_measured_hbm': by / t / 1e9 / PEAK})
+        env.close()
+        del env
     # ---- GAE: T x N x (4 r + 4 v + 1 d + 4 v[t+1 from L2] ... ) algorithmic = 17 bytes per element (r, v, d in; target, adv out)
     for (T, N) in ((128, 4104), (128, 16416)):
         r = torch.randn(T, N, device='cuda'); v = torch.randn(T, N, device='cuda'); lv = torch.randn(N, device='cuda')
