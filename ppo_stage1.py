@@ -57,6 +57,8 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
     ap.add_argument('--updates', type=int, default=None, help='stop after this many PPO updates')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--policy-path', default='policy')
+    ap.add_argument('--resume', default=None, help='checkpoint written by this trainer (e.g. policy/Stage1_40): restores the\n'
+                    'weights and, from <file>.trainer, the Adam moments / step and the sampling counter')
     ap.add_argument('--scenario', default=None, choices=[None, 'stage1', 'stage2', 'circle'],
                     help='override the world (e.g. circle: BASELINE config 4 trains on circle.world)')
     args = ap.parse_args()
@@ -92,6 +94,15 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
         logger.info('#####################################')
         logger.info('############Start Training###########')
         logger.info('#####################################')
+    if args.resume:
+        policy.load_state_dict(torch.load(args.resume, map_location=device))
+        extra = args.resume + '.trainer'
+        if os.path.exists(extra):
+            st = torch.load(extra, map_location=device)
+            opt.load_state_dict(st['optimizer'])
+            policy.sample_counter = int(st.get('sample_counter', 0))
+            if logger:
+                logger.info('resumed from %s (update %d, Adam step %d)' % (args.resume, st.get('update', -1), opt.step_count))
     hp = dict(HORIZON=HORIZON, GAMMA=GAMMA, LAMDA=LAMDA, BATCH_SIZE=batch_size, EPOCH=epoch, COEFF_ENTROPY=COEFF_ENTROPY,
               CLIP_VALUE=CLIP_VALUE, NUM_ENV=num_env, OBS_SIZE=OBS_SIZE, ACT_SIZE=ACT_SIZE, LASER_HIST=LASER_HIST,
               MAX_EPISODES=MAX_EPISODES)

@@ -49,3 +49,25 @@ def test_trainer_runs_and_logs(built, stage, tmp_path):
     assert os.path.exists(tmp_path / saved)
     sd = torch.load(tmp_path / saved)
     assert len(sd) == 23 and sd['act_fc1.weight'].shape == (256, 4096)
+
+
+def test_optimizer_state_roundtrip(built, tmp_path):
+    """What the reference never saved (ppo_stage1.py:122-126): Adam moments + step survive a save/load."""
+    from rl_collision_avoidance_b200.model.net import Adam, CNNPolicy
+    pol = CNNPolicy(seed=3, max_batch=8)
+    opt = Adam(pol.parameters(), lr=5e-5)
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    for _ in range(3):
+        pol.grad.copy_(torch.randn(pol.flat_size, device='cuda', generator=gen) * 0.01)
+        opt.step()
+    torch.save(pol.state_dict(), tmp_path / 'w')
+    torch.save({'optimizer': opt.state_dict()}, tmp_path / 'w.trainer')
+    pol2 = CNNPolicy(seed=9, max_batch=8)
+    opt2 = Adam(pol2.parameters(), lr=5e-5)
+    pol2.load_state_dict(torch.load(tmp_path / 'w'))
+    opt2.load_state_dict(torch.load(tmp_path / 'w.trainer')['optimizer'])
+    g = torch.randn(pol.flat_size, device='cuda', generator=gen) * 0.01
+    for p_, o_ in ((pol, opt), (pol2, opt2)):
+        p_.grad.copy_(g)
+        o_.step()
+    assert opt2.step_count == 4 and torch.equal(pol.flat, pol2.flat)
