@@ -70,4 +70,7 @@ def test_optimizer_state_roundtrip(built, tmp_path):
     for p_, o_ in ((pol, opt), (pol2, opt2)):
         p_.grad.copy_(g)
         o_.step()
-    assert opt2.step_count == 4 and torch.equal(pol.flat, pol2.flat)
+    assert opt2.step_count == 4
+    # compare the named tensors: the 32-float alignment padding between them is not part of a state_dict
+    for (k, a), (_, b) in zip(pol.named_parameters(), pol2.named_parameters()):
+        assert torch.equal(a, b), k
