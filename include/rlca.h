@@ -199,9 +199,13 @@ typedef struct rlca_policy rlca_policy;   /* workspace (activations kept for bac
 int64_t rlca_policy_param_offset(int32_t tensor_index);
 int64_t rlca_policy_param_size(int32_t tensor_index);     /* unpadded element count of tensor i */
 int64_t rlca_policy_launch_count(const rlca_policy *pol);
-/* fc1 forward/backward GEMMs on the tcgen05 tensor cores with 3xTF32 error compensation (default on);
- * 0 selects the plain fp32 CUDA-core GEMM (kept as the cross-check for the tensor-core path). */
+/* Conv tower + fc1 forward/backward GEMMs on the tcgen05 tensor cores with 3xTF32 error compensation
+ * (enable = 1, the default); 2 = fc1 GEMMs only; 0 selects the plain fp32 CUDA-core kernels (kept as the
+ * cross-check for the tensor-core path). */
 int rlca_policy_set_tensor_cores(rlca_policy *pol, int32_t enable);
+/* Copies the conv-tower features of the last forward, relu(conv2) flattened as c*128+q (model/net.py:42-44 `a.view`),
+ * tower 0 = actor, 1 = critic, into dst_dev (nb x 4096 floats).  Inspection hook for the parity tests. */
+int rlca_policy_features(const rlca_policy *pol, int32_t tower, int32_t nb, float *dst_dev, void *stream);
 /* Tell the workspace that params_dev changed (optimizer step, checkpoint load): derived copies of the weights
  * (tf32 hi/lo splits, transposes) are rebuilt at the next forward.  A fresh workspace starts dirty. */
 int rlca_policy_weights_changed(rlca_policy *pol);

@@ -72,6 +72,7 @@ SYMBOLS = {
     'rlca_policy_launch_count': (C.c_int64, [_P]),
     'rlca_policy_set_tensor_cores': (C.c_int, [_P, C.c_int32]),
     'rlca_policy_weights_changed': (C.c_int, [_P]),
+    'rlca_policy_features': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     'rlca_policy_create': (C.c_int, [C.c_int32, C.POINTER(_P)]),
     'rlca_policy_destroy': (C.c_int, [_P]),
     'rlca_policy_forward': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P]),

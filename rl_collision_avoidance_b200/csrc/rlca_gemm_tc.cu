@@ -23,6 +23,9 @@
 #include "../../include/rlca.h"
 #include "rlca_common.cuh"
 #include "rlca_gemm_tc.cuh"
+#include "rlca_tc_ptx.cuh"
+
+using namespace rlca_ptx;
 
 namespace {
 
@@ -36,65 +39,6 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;                 // A_hi, A_lo, B_hi,
 constexpr int TMEM_COLS = 128;
 constexpr int NUM_THREADS = 192;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(smem_addr(bar)), "r"(parity)
-                     : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), LBO unused (=1),
-// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  (cute::UMMA::SmemDescriptor.)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format TF32 (2) @7/@10, K-major both, N>>3 @17, M>>4 @24
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n)
-{
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
-{
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "setp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
-                 : "memory");
-}
 
 struct TcArgs {
     float *C[2];               // per problem (tower)
@@ -189,53 +133,50 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mAh0, const __grid_consta
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+        // TMEM -> registers (lane = row) -> this warp's 32 x 128 slab of the idle pipeline smem (pitch 132: the
+        // row-per-lane float4 stores are conflict free) -> row-wise, fully coalesced 512-byte global stores (and
+        // mask loads): a lane-per-row store would touch 32 cache lines per instruction.
         const int q = warp & 3;
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int m = m0 + q * 32 + lane;
-        float *Cp = args.C[prob] + (size_t)split * args.split_stride;
-        const float *Mp = args.mask[prob];
+        constexpr int EP = BLOCK_N + 4;
+        float *slab = reinterpret_cast<float *>(smem) + (size_t)q * 32 * EP;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
             uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
             if (nkb > 0) {
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-                               "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-                               "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-                               "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                             : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (m < args.M) {
-                const int n = n0 + c * 32;
-                float *dst = Cp + (size_t)m * args.ldc + n;
-                if (n + 32 <= args.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                               __uint_as_float(r[j + 3]));
-                        if (Mp) {
-                            const float4 mk = *reinterpret_cast<const float4 *>(Mp + (size_t)m * args.ldc + n + j);
-                            v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
-                            v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
-                        }
-                        *reinterpret_cast<float4 *>(dst + j) = v;
-                    }
-                } else {
-                    for (int j = 0; j < 32 && n + j < args.N; ++j) {
-                        float v = __uint_as_float(r[j]);
-                        if (Mp) v = Mp[(size_t)m * args.ldc + n + j] > 0.f ? v : 0.f;
-                        dst[j] = v;
-                    }
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(slab + lane * EP + c * 32 + j) = make_float4(
+                    __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+        __syncwarp();
+        float *Cp = (prob ? args.C[1] : args.C[0]) + (size_t)split * args.split_stride;
+        const float *Mp = prob ? args.mask[1] : args.mask[0];
+        const int n = n0 + lane * 4;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+            const int m = m0 + q * 32 + i;
+            if (m >= args.M) break;
+            float4 v = *reinterpret_cast<const float4 *>(slab + i * EP + lane * 4);
+            float *dst = Cp + (size_t)m * args.ldc + n;
+            if (n + 4 <= args.N) {
+                if (Mp) {
+                    const float4 mk = *reinterpret_cast<const float4 *>(Mp + (size_t)m * args.ldc + n);
+                    v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
+                    v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
                 }
+                *reinterpret_cast<float4 *>(dst) = v;
+            } else {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+                for (int j = 0; j < 4 && n + j < args.N; ++j)
+                    dst[j] = (Mp && !(Mp[(size_t)m * args.ldc + n + j] > 0.f)) ? 0.f : vv[j];
             }
         }
     }
@@ -279,6 +220,45 @@ __global__ void transpose_split_kernel(const float *__restrict__ src, int rows, 
             const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
             hi[(size_t)c * ld_out + r] = h;
             lo[(size_t)c * ld_out + r] = x - h;
+        }
+    }
+}
+
+// One pass over a [rows, cols] matrix (both towers: blockIdx.z) that writes its tf32 hi/lo split in the source layout
+// AND transposed ([cols, rows], pitch ldt): the fc1 weight feeds the forward GEMM as [256, 4096] and the dF GEMM
+// as [4096, 256], and both copies are rebuilt after every optimizer step.
+struct SplitBothArgs {
+    const float *src0, *src1;           // (selected with ?: - indexing a kernel parameter array forces a local copy)
+    float *hi0, *hi1, *lo0, *lo1, *thi0, *thi1, *tlo0, *tlo1;
+    int rows, cols, ld, ldo, ldt;      // source pitch, hi/lo pitch, transposed pitch (hi/lo may be NULL: transposed only)
+};
+__global__ void split_both_kernel(const SplitBothArgs a)
+{
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const float *src = t ? a.src1 : a.src0;
+    float *hi = t ? a.hi1 : a.hi0, *lo = t ? a.lo1 : a.lo0, *thi = t ? a.thi1 : a.thi0, *tlo = t ? a.tlo1 : a.tlo0;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        float x = 0.0f;
+        if (r < a.rows && c < a.cols) {
+            x = src[(size_t)r * a.ld + c];
+            if (hi) {
+                const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                hi[(size_t)r * a.ldo + c] = h;
+                lo[(size_t)r * a.ldo + c] = x - h;
+            }
+        }
+        tile[i][threadIdx.x] = x;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < a.cols && r < a.ldt) {
+            const float x = tile[threadIdx.x][i];
+            const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            thi[(size_t)c * a.ldt + r] = h;
+            tlo[(size_t)c * a.ldt + r] = x - h;
         }
     }
 }
@@ -378,6 +358,17 @@ void rlca_tc_transpose_split(const float *src, int rows, int cols, int ld, float
 {
     dim3 grid((cols + 31) / 32, (ld_out + 31) / 32);
     transpose_split_kernel<<<grid, dim3(32, 8), 0, s>>>(src, rows, cols, ld, hi, lo, ld_out);
+}
+
+void rlca_tc_split_both(const float *const src[2], int rows, int cols, int ld, float *const hi[2], float *const lo[2],
+                        int ldo, float *const thi[2], float *const tlo[2], int ldt, cudaStream_t s)
+{
+    SplitBothArgs a;
+    a.src0 = src[0]; a.src1 = src[1]; a.thi0 = thi[0]; a.thi1 = thi[1]; a.tlo0 = tlo[0]; a.tlo1 = tlo[1];
+    a.hi0 = hi ? hi[0] : nullptr; a.hi1 = hi ? hi[1] : nullptr; a.lo0 = lo ? lo[0] : nullptr; a.lo1 = lo ? lo[1] : nullptr;
+    a.rows = rows; a.cols = cols; a.ld = ld; a.ldo = ldo; a.ldt = ldt;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, 2);
+    split_both_kernel<<<grid, dim3(32, 8), 0, s>>>(a);
 }
 
 void rlca_tc_splitk_bias_relu(const float *P, int splits, long long split_stride, long long tower_stride,

@@ -16,6 +16,10 @@ int rlca_tc_gemm(const RlcaTcProblem *pr, int nprob, int M, int N, int K, int ld
                  cudaStream_t s);
 void rlca_tc_split(const float *src, int rows, int cols, int ld, float *hi, float *lo, int ld_out, cudaStream_t s);
 void rlca_tc_transpose_split(const float *src, int rows, int cols, int ld, float *hi, float *lo, int ld_out, cudaStream_t s);
+// both towers in one launch: hi/lo split in the source layout (pitch ldo; hi = lo = NULL skips it) and transposed
+// ([cols, rows], pitch ldt, zero-filled beyond `rows`)
+void rlca_tc_split_both(const float *const src[2], int rows, int cols, int ld, float *const hi[2], float *const lo[2],
+                        int ldo, float *const thi[2], float *const tlo[2], int ldt, cudaStream_t s);
 void rlca_tc_splitk_bias_relu(const float *P, int splits, long long split_stride, long long tower_stride,
                               const float *bias0, const float *bias1, int M, int N, float *X0, float *X1, int ldx,
                               cudaStream_t s);

@@ -17,6 +17,7 @@
 #include "../../include/rlca.h"
 #include "rlca_common.cuh"
 #include "rlca_gemm_tc.cuh"
+#include "rlca_conv_tc.cuh"
 
 // ------------------------------------------------------------------------------------ layout
 static const int64_t kTensorSize[RLCA_POLICY_NTENSORS] = {
@@ -102,6 +103,9 @@ struct rlca_policy {
     float *dZTs;     // [2][hi,lo][256][bpad]
     float *FTs;      // [2][hi,lo][4096][bpad]
     float *P;        // split-K partials [splits<=8][2][B][256]
+    int use_tc_conv; // conv tower on tcgen05 (rlca_conv_tc.cu); needs use_tc (it feeds the fc1 GEMM's hi/lo split)
+    int num_sms;
+    float *Wimg;     // pre-swizzled tf32 hi/lo image of the conv weights for the tensor-core conv tower
     int64_t launches;
 };
 
@@ -269,7 +273,8 @@ __global__ void __launch_bounds__(256) conv_tower_fwd_kernel(const float *__rest
 }
 
 // ------------------------------------------------------------------------------------ conv tower backward
-// One CTA per (CONV_SPC samples, tower), 256 threads.  dF (already masked by relu(conv2)) is d(conv2 pre-activation).
+// One CTA per (CONV_SPC samples, tower), 256 threads.  dF is d(relu(conv2)) - masked here by Fmask > 0, or already
+// masked by the producing GEMM when Fmask is NULL.
 // Shared-memory layouts are chosen so that every hot loop reads conflict-free or by broadcast:
 //   g2t[p][co] / g1t[s][co]  position-major with pitch 33 (lanes over co: consecutive; lanes over p: stride 33)
 //   h1e / h1o                channel-major even/odd split as in the forward kernel (read by broadcast here)
@@ -288,6 +293,7 @@ struct ConvBwdSmem {
 
 __global__ void __launch_bounds__(256) conv_tower_bwd_kernel(const float *__restrict__ obs, const float *__restrict__ Wc,
                                                              TowerPtrs ta, TowerPtrs tc, const float *__restrict__ dF,
+                                                             const float *__restrict__ Fmask,
                                                              float *__restrict__ part, int nb)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -316,7 +322,13 @@ __global__ void __launch_bounds__(256) conv_tower_bwd_kernel(const float *__rest
             sm.xo[c][h] = (jo >= 1 && jo <= 512) ? obs_n[c * 512 + jo - 1] : 0.0f;
         }
         const float *dF_n = dF + ((size_t)t * nb + n) * FEAT;
-        for (int i = tid; i < 4096; i += 256) sm.g2t[i & 127][i >> 7] = dF_n[i];     // coalesced read, stride-33 write
+        // coalesced read, stride-33 write; the relu(conv2) mask is applied here when the dF GEMM left it to us
+        if (Fmask) {
+            const float *F_n = Fmask + ((size_t)t * nb + n) * FEAT;
+            for (int i = tid; i < 4096; i += 256) sm.g2t[i & 127][i >> 7] = F_n[i] > 0.0f ? dF_n[i] : 0.0f;
+        } else {
+            for (int i = tid; i < 4096; i += 256) sm.g2t[i & 127][i >> 7] = dF_n[i];
+        }
         if (tid < 33) sm.g2t[128][tid] = 0.0f;
         __syncthreads();
         // ---- recompute h1 = relu(conv1(x)): thread = position (255 of them)
@@ -516,68 +528,82 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    for (int k0 = kbeg; k0 < kend; k0 += 16) {
-        // ---- A tile -> As[k][m]
+    // global -> registers (one float4 of the A tile and one of the B tile per thread), registers -> shared;
+    // the fetch of tile k+1 is issued before the FMAs of tile k so its latency hides behind them
+    auto fetch = [&](int k0, float4 &va, float4 &vb) {
+        va = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb = va;
         if (!TA) {
             const int m = tid >> 2, kq = (tid & 3) * 4;            // 64 rows x 4 float4 along k
             const int gm = m0 + m, gk = k0 + kq;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gm < g.M) {
                 const float *src = pr.A + (size_t)gm * g.lda + gk;
-                if (gk + 3 < kend) v = *reinterpret_cast<const float4 *>(src);
+                if (gk + 3 < kend) va = *reinterpret_cast<const float4 *>(src);
                 else {
-                    if (gk + 0 < kend) v.x = src[0];
-                    if (gk + 1 < kend) v.y = src[1];
-                    if (gk + 2 < kend) v.z = src[2];
+                    if (gk + 0 < kend) va.x = src[0];
+                    if (gk + 1 < kend) va.y = src[1];
+                    if (gk + 2 < kend) va.z = src[2];
                 }
             }
-            As[kq + 0][m] = v.x; As[kq + 1][m] = v.y; As[kq + 2][m] = v.z; As[kq + 3][m] = v.w;
         } else {
             const int k = tid >> 4, mq = (tid & 15) * 4;           // 16 k x 16 float4 along m
             const int gk = k0 + k, gm = m0 + mq;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gk < kend) {
                 const float *src = pr.A + (size_t)gk * g.lda + gm;
-                if (gm + 3 < g.M) v = *reinterpret_cast<const float4 *>(src);
+                if (gm + 3 < g.M) va = *reinterpret_cast<const float4 *>(src);
                 else {
-                    if (gm + 0 < g.M) v.x = src[0];
-                    if (gm + 1 < g.M) v.y = src[1];
-                    if (gm + 2 < g.M) v.z = src[2];
+                    if (gm + 0 < g.M) va.x = src[0];
+                    if (gm + 1 < g.M) va.y = src[1];
+                    if (gm + 2 < g.M) va.z = src[2];
                 }
             }
-            *reinterpret_cast<float4 *>(&As[k][mq]) = v;
         }
-        // ---- B tile -> Bs[k][n]
         if (TB) {
             const int n = tid >> 2, kq = (tid & 3) * 4;
             const int gn = n0 + n, gk = k0 + kq;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gn < g.N) {
                 const float *src = pr.B + (size_t)gn * g.ldb + gk;
-                if (gk + 3 < kend) v = *reinterpret_cast<const float4 *>(src);
+                if (gk + 3 < kend) vb = *reinterpret_cast<const float4 *>(src);
                 else {
-                    if (gk + 0 < kend) v.x = src[0];
-                    if (gk + 1 < kend) v.y = src[1];
-                    if (gk + 2 < kend) v.z = src[2];
+                    if (gk + 0 < kend) vb.x = src[0];
+                    if (gk + 1 < kend) vb.y = src[1];
+                    if (gk + 2 < kend) vb.z = src[2];
                 }
             }
-            Bs[kq + 0][n] = v.x; Bs[kq + 1][n] = v.y; Bs[kq + 2][n] = v.z; Bs[kq + 3][n] = v.w;
         } else {
             const int k = tid >> 4, nq = (tid & 15) * 4;
             const int gk = k0 + k, gn = n0 + nq;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gk < kend) {
                 const float *src = pr.B + (size_t)gk * g.ldb + gn;
-                if (gn + 3 < g.N) v = *reinterpret_cast<const float4 *>(src);
+                if (gn + 3 < g.N) vb = *reinterpret_cast<const float4 *>(src);
                 else {
-                    if (gn + 0 < g.N) v.x = src[0];
-                    if (gn + 1 < g.N) v.y = src[1];
-                    if (gn + 2 < g.N) v.z = src[2];
+                    if (gn + 0 < g.N) vb.x = src[0];
+                    if (gn + 1 < g.N) vb.y = src[1];
+                    if (gn + 2 < g.N) vb.z = src[2];
                 }
             }
-            *reinterpret_cast<float4 *>(&Bs[k][nq]) = v;
         }
+    };
+    auto stash = [&](const float4 &va, const float4 &vb) {
+        if (!TA) {
+            const int m = tid >> 2, kq = (tid & 3) * 4;
+            As[kq + 0][m] = va.x; As[kq + 1][m] = va.y; As[kq + 2][m] = va.z; As[kq + 3][m] = va.w;
+        } else {
+            *reinterpret_cast<float4 *>(&As[tid >> 4][(tid & 15) * 4]) = va;
+        }
+        if (TB) {
+            const int n = tid >> 2, kq = (tid & 3) * 4;
+            Bs[kq + 0][n] = vb.x; Bs[kq + 1][n] = vb.y; Bs[kq + 2][n] = vb.z; Bs[kq + 3][n] = vb.w;
+        } else {
+            *reinterpret_cast<float4 *>(&Bs[tid >> 4][(tid & 15) * 4]) = vb;
+        }
+    };
+    float4 va, vb;
+    if (kbeg < kend) fetch(kbeg, va, vb);
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+        stash(va, vb);
         __syncthreads();
+        if (k0 + 16 < kend) fetch(k0 + 16, va, vb);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
@@ -690,15 +716,24 @@ __global__ void __launch_bounds__(128) heads_bwd_kernel(const float *__restrict_
     if (j == 0) { o[0 * 132 + 128] = b1; o[1 * 132 + 128] = b2; o[2 * 132 + 128] = b3; }
 }
 
-__global__ void heads_part_reduce_kernel(const float *__restrict__ headpart, int chunks, float *ga1w, float *ga1b,
-                                         float *ga2w, float *ga2b, float *gcw, float *gcb)
+#define HPR_GROUPS 7      // 7 x 132 = 924 threads: each group sums every 7th chunk, fixed-order combine (deterministic)
+__global__ void __launch_bounds__(HPR_GROUPS * 132)
+heads_part_reduce_kernel(const float *__restrict__ headpart, int chunks, float *ga1w, float *ga1b, float *ga2w,
+                         float *ga2b, float *gcw, float *gcb)
 {
-    const int j = threadIdx.x, h = blockIdx.x;     // 129 active threads, 3 blocks
-    if (j > 128) return;
+    __shared__ float red[HPR_GROUPS][132];
+    const int g = threadIdx.x / 132, j = threadIdx.x - g * 132, h = blockIdx.x;     // 3 blocks: actor1, actor2, critic
     float acc = 0.f;
-    for (int c = 0; c < chunks; ++c) acc += headpart[((size_t)c * 3 + h) * 132 + j];
-    float *w = h == 0 ? ga1w : (h == 1 ? ga2w : gcw), *b = h == 0 ? ga1b : (h == 1 ? ga2b : gcb);
-    if (j < 128) w[j] = acc; else b[0] = acc;
+    if (j <= 128)
+        for (int c = g; c < chunks; c += HPR_GROUPS) acc += headpart[((size_t)c * 3 + h) * 132 + j];
+    red[g][j] = acc;
+    __syncthreads();
+    if (g == 0 && j <= 128) {
+#pragma unroll
+        for (int k = 1; k < HPR_GROUPS; ++k) acc += red[k][j];
+        float *w = h == 0 ? ga1w : (h == 1 ? ga2w : gcw), *b = h == 0 ? ga1b : (h == 1 ? ga2b : gcb);
+        if (j < 128) w[j] = acc; else b[0] = acc;
+    }
 }
 
 // out[t][j] = sum_i A[t][i*ld + j] ; grid (ceil(ncols/32), ntowers), 256 threads = 8 row groups x 32 columns
@@ -712,7 +747,10 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColsumArgs a)
     const int rper = (a.rows + gridDim.z - 1) / gridDim.z;
     const int r0 = blockIdx.z * rper, r1 = min(a.rows, r0 + rper);
     if (j < a.cols)
-        for (int i = r0 + rg; i < r1; i += 8) acc += a.A[t][(size_t)i * a.ld + j];
+        {
+        const float *A = t ? a.A[1] : a.A[0];
+        for (int i = r0 + rg; i < r1; i += 8) acc += A[(size_t)i * a.ld + j];
+    }
     red[rg][lane] = acc;
     __syncthreads();
     if (rg == 0 && j < a.cols) {
@@ -1039,6 +1077,13 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
         if (rc) return rc;
         p->use_tc = 1;
         p->weights_dirty = 1;
+        rc = rlca_conv_tc_init();
+        if (rc) return rc;
+        RLCA_CUDA_TRY(cudaMalloc(&p->Wimg, rlca_conv_tc_image_floats() * sizeof(float)));
+        int dev = 0;
+        RLCA_CUDA_TRY(cudaGetDevice(&dev));
+        RLCA_CUDA_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
+        p->use_tc_conv = 1;
     }
     RLCA_CUDA_TRY(cudaFuncSetAttribute(conv_tower_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(ConvSmem)));
@@ -1053,7 +1098,7 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
     if (!p) return RLCA_OK;
     cudaFree(p->F); cudaFree(p->X); cudaFree(p->H2); cudaFree(p->dOut); cudaFree(p->dZ2); cudaFree(p->dX);
     cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red); cudaFree(p->S); cudaFree(p->Wc);
-    cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P);
+    cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P); cudaFree(p->Wimg);
     delete p;
     return RLCA_OK;
 }
@@ -1071,7 +1116,18 @@ extern "C" int rlca_policy_set_tensor_cores(rlca_policy *p, int32_t enable)
 {
     if (!p) return rlca_set_err(RLCA_ERR_INVALID, "policy is NULL");
     p->use_tc = enable ? 1 : 0;
+    p->use_tc_conv = enable == 1 ? 1 : 0;      // 2 = fc1 GEMMs only (conv tower on the CUDA cores)
     p->weights_dirty = 1;
+    return RLCA_OK;
+}
+
+extern "C" int rlca_policy_features(const rlca_policy *pol, int32_t tower, int32_t nb, float *dst_dev, void *stream)
+{
+    if (!pol || !dst_dev || tower < 0 || tower > 1 || nb < 1 || nb > pol->max_batch)
+        return rlca_set_err(RLCA_ERR_INVALID, "rlca_policy_features: bad argument");
+    // F is [2][nb of the last forward][4096]; the caller passes the same nb
+    RLCA_CUDA_TRY(cudaMemcpyAsync(dst_dev, pol->F + (size_t)tower * nb * FEAT, (size_t)nb * FEAT * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return RLCA_OK;
 }
 
@@ -1083,8 +1139,20 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
     cudaStream_t s = (cudaStream_t)stream;
     const TowerPtrs ta = tower_ptrs(params, 0), tc = tower_ptrs(params, 1);
     if (pol->weights_dirty) conv_prep_weights_kernel<<<dim3((CONV_WBLK + 255) / 256, 2), 256, 0, s>>>(ta, tc, pol->Wc);
-    conv_tower_fwd_kernel<<<(nb + CONV_SPC - 1) / CONV_SPC, 256, sizeof(ConvSmem), s>>>(obs, pol->Wc, pol->F,
-                                                                                     pol->use_tc ? pol->Fs : nullptr, nb);
+    // the tensor-core conv tower stages the scan with 16-byte bulk copies; oddly aligned inputs take the CUDA-core kernel
+    if (pol->use_tc && pol->use_tc_conv && ((uintptr_t)obs & 15) == 0) {
+        if (pol->weights_dirty) {
+            const float *w1[2] = {ta.cv1w, tc.cv1w}, *b1[2] = {ta.cv1b, tc.cv1b};
+            const float *w2[2] = {ta.cv2w, tc.cv2w}, *b2[2] = {ta.cv2b, tc.cv2b};
+            rlca_conv_tc_prep(w1, b1, w2, b2, pol->Wimg, s);
+            pol->launches += 1;
+        }
+        int rc = rlca_conv_tc_forward(obs, pol->Wimg, pol->F, pol->Fs, nb, pol->num_sms, s);
+        if (rc) return rc;
+    } else {
+        conv_tower_fwd_kernel<<<(nb + CONV_SPC - 1) / CONV_SPC, 256, sizeof(ConvSmem), s>>>(
+            obs, pol->Wc, pol->F, pol->use_tc ? pol->Fs : nullptr, nb);
+    }
     GemmArgs g{};
     if (pol->use_tc) {
         // fc1 on the tensor cores: split F and W1 into tf32 hi/lo parts, split-K 3xTF32 GEMM, fused bias+ReLU reduce
@@ -1094,13 +1162,16 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
         for (int t = 0; t < 2; ++t) {
             float *Fh = pol->Fs + (size_t)(2 * t) * B * FEAT, *Fl = Fh + B * FEAT;
             float *Wh = pol->W1s + (size_t)(2 * t) * WSZ, *Wl = Wh + WSZ;
-            const float *w = t == 0 ? ta.fc1w : tc.fc1w;
-            if (pol->weights_dirty) {      // hi/lo (and transposed) copies of W1 are refreshed only after a weight change
-                rlca_tc_split(w, 256, FEAT, FEAT, Wh, Wl, FEAT, s);
-                rlca_tc_transpose_split(w, 256, FEAT, FEAT, pol->W1Ts + (size_t)(2 * t) * WSZ,
-                                        pol->W1Ts + (size_t)(2 * t + 1) * WSZ, 256, s);
-            }
             pr[t] = RlcaTcProblem{Fh, Fl, Wh, Wl, FEAT, FEAT, pol->P + (size_t)t * B * 256, nullptr};
+        }
+        if (pol->weights_dirty) {          // hi/lo (and transposed) copies of W1 are refreshed only after a weight change
+            const float *w[2] = {ta.fc1w, tc.fc1w};
+            float *hi[2], *lo[2], *thi[2], *tlo[2];
+            for (int t = 0; t < 2; ++t) {
+                hi[t] = pol->W1s + (size_t)(2 * t) * WSZ; lo[t] = hi[t] + WSZ;
+                thi[t] = pol->W1Ts + (size_t)(2 * t) * WSZ; tlo[t] = thi[t] + WSZ;
+            }
+            rlca_tc_split_both(w, 256, FEAT, FEAT, hi, lo, FEAT, thi, tlo, 256, s);
         }
         const int mtiles = (nb + 127) / 128;
         int splits = 1;
@@ -1110,7 +1181,7 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
         if (rc) return rc;
         rlca_tc_splitk_bias_relu(pol->P, splits, split_stride, (long long)nb * 256, ta.fc1b, tc.fc1b, nb, 256, pol->X,
                                  pol->X + (size_t)nb * XLD, XLD, s);
-        pol->launches += pol->weights_dirty ? 6 : 2;
+        pol->launches += pol->weights_dirty ? 3 : 2;
     } else {
         // fc1: X[:, :256] = relu(F W1^T + b1)
         g.M = nb; g.N = 256; g.K = FEAT; g.lda = FEAT; g.ldb = FEAT; g.ldc = XLD; g.relu = 1;
@@ -1176,7 +1247,7 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     heads_bwd_kernel<<<chunks, 128, 0, s>>>(pol->H2, pol->dOut, params + tensor_offset(T_A1W),
                                             params + tensor_offset(T_A2W), params + tensor_offset(T_CRITW), nb, pol->dZ2,
                                             pol->headpart);
-    heads_part_reduce_kernel<<<3, 160, 0, s>>>(pol->headpart, chunks, grads + tensor_offset(T_A1W),
+    heads_part_reduce_kernel<<<3, HPR_GROUPS * 132, 0, s>>>(pol->headpart, chunks, grads + tensor_offset(T_A1W),
                                                grads + tensor_offset(T_A1B), grads + tensor_offset(T_A2W),
                                                grads + tensor_offset(T_A2B), grads + tensor_offset(T_CRITW),
                                                grads + tensor_offset(T_CRITB));
@@ -1210,25 +1281,28 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
         const size_t WSZ = (size_t)256 * FEAT;
         const size_t BP = (size_t)((nb + 31) / 32 * 32);
         RlcaTcProblem pw[2], pf[2];
+        const float *dzsrc[2], *fsrc[2];
+        float *dzh[2], *dzl[2], *dzth[2], *dztl[2], *fth[2], *ftl[2];
         for (int t = 0; t < 2; ++t) {
-            const float *dz = pol->dX + (size_t)t * B * XLD;                       // dZ1 [nb,256], pitch 260
-            float *dzh = pol->dZs + (size_t)(2 * t) * B * 256, *dzl = dzh + B * 256;
-            float *dzth = pol->dZTs + (size_t)(2 * t) * 256 * BP, *dztl = dzth + 256 * BP;
-            float *fth = pol->FTs + (size_t)(2 * t) * FEAT * BP, *ftl = fth + FEAT * BP;
-            rlca_tc_split(dz, nb, 256, XLD, dzh, dzl, 256, s);
-            rlca_tc_transpose_split(dz, nb, 256, XLD, dzth, dztl, (int)BP, s);
-            rlca_tc_transpose_split(pol->F + (size_t)t * B * FEAT, nb, FEAT, FEAT, fth, ftl, (int)BP, s);
+            dzsrc[t] = pol->dX + (size_t)t * B * XLD;                              // dZ1 [nb,256], pitch 260
+            fsrc[t] = pol->F + (size_t)t * B * FEAT;
+            dzh[t] = pol->dZs + (size_t)(2 * t) * B * 256; dzl[t] = dzh[t] + B * 256;
+            dzth[t] = pol->dZTs + (size_t)(2 * t) * 256 * BP; dztl[t] = dzth[t] + 256 * BP;
+            fth[t] = pol->FTs + (size_t)(2 * t) * FEAT * BP; ftl[t] = fth[t] + FEAT * BP;
             // dW_fc1 (256 x 4096) = dZ1^T F : A = dZ1^T [256, nb], B = F^T [4096, nb]
-            pw[t] = RlcaTcProblem{dzth, dztl, fth, ftl, (int)BP, (int)BP, t == 0 ? ga.fc1w : gc.fc1w, nullptr};
-            // dF (nb x 4096) = dZ1 W_fc1 : A = dZ1 [nb,256], B = W1^T [4096,256]; masked by relu(conv2)
-            pf[t] = RlcaTcProblem{dzh, dzl, pol->W1Ts + (size_t)(2 * t) * WSZ, pol->W1Ts + (size_t)(2 * t + 1) * WSZ, 256, 256,
-                                  pol->dF + (size_t)t * B * FEAT, pol->F + (size_t)t * B * FEAT};
+            pw[t] = RlcaTcProblem{dzth[t], dztl[t], fth[t], ftl[t], (int)BP, (int)BP, t == 0 ? ga.fc1w : gc.fc1w, nullptr};
+            // dF (nb x 4096) = dZ1 W_fc1 : A = dZ1 [nb,256], B = W1^T [4096,256]; the relu(conv2) mask is applied by the
+            // consumer (conv_tower_bwd) so this output-bound GEMM's epilogue is a pure coalesced store
+            pf[t] = RlcaTcProblem{dzh[t], dzl[t], pol->W1Ts + (size_t)(2 * t) * WSZ, pol->W1Ts + (size_t)(2 * t + 1) * WSZ, 256, 256,
+                                  pol->dF + (size_t)t * B * FEAT, nullptr};
         }
+        rlca_tc_split_both(dzsrc, nb, 256, XLD, dzh, dzl, 256, dzth, dztl, (int)BP, s);
+        rlca_tc_split_both(fsrc, nb, FEAT, FEAT, nullptr, nullptr, 0, fth, ftl, (int)BP, s);
         int rc = rlca_tc_gemm(pw, 2, 256, FEAT, nb, FEAT, 1, 0, s);
         if (rc) return rc;
         rc = rlca_tc_gemm(pf, 2, nb, FEAT, 256, FEAT, 1, 0, s);
         if (rc) return rc;
-        pol->launches += 8;
+        pol->launches += 4;
     } else {
     // dW_fc1 (256 x 4096) = dZ1^T F
     g.M = 256; g.N = FEAT; g.K = nb; g.lda = XLD; g.ldb = FEAT; g.ldc = FEAT; g.relu = 0;
@@ -1242,6 +1316,7 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     launch_gemm<false, false>(g, 2, s);
     }
     conv_tower_bwd_kernel<<<dim3((nb + CONV_SPC - 1) / CONV_SPC, 2), 256, sizeof(ConvBwdSmem), s>>>(obs, pol->Wc, ta, tc, pol->dF,
+                                                                                                 pol->use_tc ? pol->F : nullptr,
                                                                                                  pol->part, nb);
     conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(pol->part, nb, pol->S);
     conv_part_final_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->S, RSPLIT, ga, gc);

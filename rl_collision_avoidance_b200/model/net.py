@@ -135,10 +135,17 @@ class CNNPolicy:
         return self._ws
 
     def set_tensor_cores(self, enable=True):
-        """fc1 GEMMs on tcgen05 with 3xTF32 compensation (default) or on the fp32 CUDA-core GEMM."""
-        self.tensor_cores = bool(enable)
+        """Conv tower + fc1 GEMMs on tcgen05 with 3xTF32 compensation (True, default), fc1 GEMMs only (2),
+        or everything on the fp32 CUDA-core kernels (False)."""
+        self.tensor_cores = 2 if enable == 2 and enable is not True else bool(enable)
         if self._ws is not None:
             _lib.check(self.lib.rlca_policy_set_tensor_cores(self._ws, int(self.tensor_cores)))
+
+    def features(self, tower, nb):
+        """relu(conv2) features (nb, 4096) of the last forward, tower 0 actor / 1 critic (inspection hook)."""
+        out = torch.empty(nb, 4096, device=self.device)
+        _lib.check(self.lib.rlca_policy_features(self._ws, tower, nb, _ptr(out), self._stream()))
+        return out
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
