@@ -106,6 +106,8 @@ struct rlca_policy {
     int use_tc_conv; // conv tower on tcgen05 (rlca_conv_tc.cu); needs use_tc (it feeds the fc1 GEMM's hi/lo split)
     int num_sms;
     float *Wimg;     // pre-swizzled tf32 hi/lo image of the conv weights for the tensor-core conv tower
+    float *WimgB;    // same for the backward kernel (per tower: conv1 weights | conv2 weights regrouped by tap)
+    int conv_bwd_dirty;
     int64_t launches;
 };
 
@@ -1058,7 +1060,7 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
     RLCA_CUDA_TRY(cudaMalloc(&p->dZ2, 2 * B * 128 * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->dX, 2 * B * XLD * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->dF, 2 * B * FEAT * sizeof(float)));
-    RLCA_CUDA_TRY(cudaMalloc(&p->part, 2 * B * CONV_PART * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->part, 2 * (B > 128 ? B : 128) * CONV_PART * sizeof(float)));   // >= one slot per CTA of the tc backward
     RLCA_CUDA_TRY(cudaMalloc(&p->headpart, (size_t)chunks * 3 * 132 * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->red, 64 * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->Wc, 2 * CONV_WBLK * sizeof(float)));
@@ -1080,6 +1082,8 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
         rc = rlca_conv_tc_init();
         if (rc) return rc;
         RLCA_CUDA_TRY(cudaMalloc(&p->Wimg, rlca_conv_tc_image_floats() * sizeof(float)));
+        RLCA_CUDA_TRY(cudaMalloc(&p->WimgB, rlca_conv_tc_bwd_image_floats() * sizeof(float)));
+        p->conv_bwd_dirty = 1;
         int dev = 0;
         RLCA_CUDA_TRY(cudaGetDevice(&dev));
         RLCA_CUDA_TRY(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1098,7 +1102,7 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
     if (!p) return RLCA_OK;
     cudaFree(p->F); cudaFree(p->X); cudaFree(p->H2); cudaFree(p->dOut); cudaFree(p->dZ2); cudaFree(p->dX);
     cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red); cudaFree(p->S); cudaFree(p->Wc);
-    cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P); cudaFree(p->Wimg);
+    cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P); cudaFree(p->Wimg); cudaFree(p->WimgB);
     delete p;
     return RLCA_OK;
 }
@@ -1109,6 +1113,7 @@ extern "C" int rlca_policy_weights_changed(rlca_policy *p)
 {
     if (!p) return rlca_set_err(RLCA_ERR_INVALID, "policy is NULL");
     p->weights_dirty = 1;
+    p->conv_bwd_dirty = 1;
     return RLCA_OK;
 }
 
@@ -1118,6 +1123,7 @@ extern "C" int rlca_policy_set_tensor_cores(rlca_policy *p, int32_t enable)
     p->use_tc = enable ? 1 : 0;
     p->use_tc_conv = enable == 1 ? 1 : 0;      // 2 = fc1 GEMMs only (conv tower on the CUDA cores)
     p->weights_dirty = 1;
+    p->conv_bwd_dirty = 1;
     return RLCA_OK;
 }
 
@@ -1315,10 +1321,24 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     g.pr[1] = GemmProblem{pol->dX + B * XLD, tc.fc1w, nullptr, pol->F + B * FEAT, pol->dF + B * FEAT};
     launch_gemm<false, false>(g, 2, s);
     }
-    conv_tower_bwd_kernel<<<dim3((nb + CONV_SPC - 1) / CONV_SPC, 2), 256, sizeof(ConvBwdSmem), s>>>(obs, pol->Wc, ta, tc, pol->dF,
-                                                                                                 pol->use_tc ? pol->F : nullptr,
-                                                                                                 pol->part, nb);
-    conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(pol->part, nb, pol->S);
+    if (pol->use_tc && pol->use_tc_conv && ((uintptr_t)obs & 15) == 0) {
+        // conv tower backward on the tensor cores: one partial per CTA instead of one per sample
+        if (pol->conv_bwd_dirty) {
+            const float *w1[2] = {ta.cv1w, tc.cv1w}, *b1[2] = {ta.cv1b, tc.cv1b};
+            const float *w2[2] = {ta.cv2w, tc.cv2w}, *b2[2] = {ta.cv2b, tc.cv2b};
+            rlca_conv_tc_bwd_prep(w1, b1, w2, b2, pol->WimgB, s);
+            pol->conv_bwd_dirty = 0;
+            pol->launches += 1;
+        }
+        int rc = rlca_conv_tc_backward(obs, pol->WimgB, pol->dF, pol->F, pol->part, nb, pol->num_sms, s);
+        if (rc) return rc;
+        conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(
+            pol->part, rlca_conv_tc_bwd_slots(nb, pol->num_sms), pol->S);
+    } else {
+        conv_tower_bwd_kernel<<<dim3((nb + CONV_SPC - 1) / CONV_SPC, 2), 256, sizeof(ConvBwdSmem), s>>>(
+            obs, pol->Wc, ta, tc, pol->dF, pol->use_tc ? pol->F : nullptr, pol->part, nb);
+        conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(pol->part, nb, pol->S);
+    }
     conv_part_final_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->S, RSPLIT, ga, gc);
     pol->launches += 10;
     RLCA_CUDA_TRY(cudaGetLastError());
