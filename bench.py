@@ -154,6 +154,51 @@ def run_cpu(steps, warmup, budget_s, threads=None):
     return val, cores, sample, dt / steps * 1e3
 
 
+def time_learner(dev, n_agents):
+    """Side measurement (outside the timed env region, CUDA events): the policy forward at the rollout batch and one
+    PPO minibatch step (forward, loss, backward, Adam) at the reference's batch size 1024 (ppo_stage1.py:28)."""
+    import torch
+    from rl_collision_avoidance_b200 import _lib
+    from rl_collision_avoidance_b200.model.net import Adam, CNNPolicy, _ptr
+    pol = CNNPolicy(device=str(dev), max_batch=max(n_agents, 1024), seed=0)
+    opt = Adam(pol.parameters(), lr=5e-5)
+    lib = pol.lib
+
+    def timeit(fn, n=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n * 1e3
+
+    out = {'tensor_cores': 'tcgen05 3xTF32: conv tower forward/backward + fc1 forward/dW/dX'}
+    for nb, key in ((n_agents, 'policy_forward_us'), (1024, 'ppo_minibatch_step_us')):
+        obs = torch.rand(nb, 1536, device=dev) - 0.5
+        gs = torch.rand(nb, 4, device=dev)
+        v, mean = torch.empty(nb, device=dev), torch.empty(nb, 2, device=dev)
+        act, lp = torch.rand(nb, 2, device=dev), torch.rand(nb, device=dev) - 1
+        adv, tgt, losses = torch.randn(nb, device=dev), torch.randn(nb, device=dev), torch.zeros(3, device=dev)
+        ws, st = pol._workspace(nb), pol._stream()
+
+        def fwd():
+            _lib.check(lib.rlca_policy_forward(ws, _ptr(pol.flat), _ptr(obs), _ptr(gs), nb, _ptr(v), _ptr(mean), st))
+
+        def step():
+            fwd()
+            _lib.check(lib.rlca_ppo_loss_fwd_bwd(ws, _ptr(pol.flat), _ptr(v), _ptr(mean), _ptr(act), _ptr(lp), _ptr(adv),
+                                                 _ptr(tgt), nb, 0.1, 5e-4, 20.0, _ptr(losses), st))
+            _lib.check(lib.rlca_policy_backward(ws, _ptr(pol.flat), _ptr(obs), _ptr(gs), nb, _ptr(pol.grad), st))
+            opt.step()
+
+        out[key] = {'batch': nb, 'us': timeit(fwd if key == 'policy_forward_us' else step)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -312,6 +357,8 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
+        if world_size == 1:
+            line['learner'] = time_learner(dev, N)
         if world_size == 1 and not args.no_cpu:
             val, cores, sample, _ = run_cpu(args.cpu_steps, 3, budget_s=25.0)
             line['cpu_baseline'] = {'value': val, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port',
