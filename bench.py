@@ -8,8 +8,8 @@ raycast + reward/done + obs) over the per-GPU agent batch: 171 stage-1 worlds x 
 data-path collective (worlds are independent).
 
   value        whole-job agent-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e          same metric through the host-buffer C-ABI call (pinned action H2D, tick,
-               obs/reward/flags/gs D2H, sync) — the reference-facing call
+  e2e          same metric through the host-buffer C-ABI call (pinned action H2D, tick in world
+               ranges with the scans' D2H overlapped, reward/flags/gs D2H, sync) — the reference-facing call
   roofline     algorithmic bytes (4*B+96 per agent-step) / measured launch time
                vs the measured HBM copy peak (MEASURED_PEAKS.json, else the 6650 GB/s fallback)
   cpu_baseline the CPU oracle (port of the reference semantics) on the host cores, bounded sample
@@ -207,6 +207,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--e2e-steps', type=int, default=200)
     ap.add_argument('--cpu-steps', type=int, default=40)
+    ap.add_argument('--e2e-sweep', action='store_true', help='also time step_host for several host-chunk counts')
     ap.add_argument('--ctas-per-world', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
@@ -293,33 +294,32 @@ def main():
     ms_max = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: the host-buffer call, strictly serial (copy in, tick, copy out, sync)
+    # ---- e2e: the host-buffer call (pinned action H2D, tick, obs/reward/flags/gs D2H, sync inside every call)
     a_host = [torch.from_numpy(random_actions(rng, N)).pin_memory() for _ in range(8)]
-    for i in range(5):
-        env.step_host(a_host[i % 8])
-    sync()
-    t0 = time.perf_counter()
-    for i in range(args.e2e_steps):
-        env.step_host(a_host[i % 8])
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = N * world_size * args.e2e_steps / float(te.item())
+
+    def time_e2e(want_obs=True, chunks=0):
+        env.set_host_chunks(chunks)
+        for i in range(5):
+            env.step_host(a_host[i % 8], want_obs=want_obs)
+        sync()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            env.step_host(a_host[i % 8], want_obs=want_obs)
+        torch.cuda.synchronize(dev)
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world_size > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        env.set_host_chunks(0)
+        return N * world_size * args.e2e_steps / float(te.item())
+
+    e2e_val = time_e2e()                         # library default: ticked in world ranges, scans overlap the next range
+    e2e_serial = time_e2e(chunks=1)              # copy in, one launch, copy out (the round-1 number, for comparison)
     # variant for callers that keep the policy on the device: same call, but the observations stay in HBM
     # (action H2D + tick + reward/flags/goal-speed D2H + sync).  Reported next to `e2e`, never instead of it.
-    for i in range(5):
-        env.step_host(a_host[i % 8], want_obs=False)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for i in range(args.e2e_steps):
-        env.step_host(a_host[i % 8], want_obs=False)
-    torch.cuda.synchronize(dev)
-    tn = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
-    e2e_noobs = N * world_size * args.e2e_steps / float(tn.item())
+    e2e_noobs = time_e2e(want_obs=False)
+    e2e_sweep = None
+    if args.e2e_sweep:
+        e2e_sweep = {str(k): time_e2e(chunks=k) for k in (1, 2, 3, 4, 6, 8, 12, 16, -1)}
 
     if rank == 0:
         value = N * world_size * args.steps / (ms_max * 1e-3)
@@ -350,13 +350,18 @@ def main():
                          'algorithmic_bytes_per_launch': N * alg_bytes(BEAMS),
                          'note': 'per-GPU; the march is issue/shared-memory bound, not HBM bound (DESIGN.md §6)'},
             'e2e': {'value': e2e_val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': N * 8 * world_size,
-                    'd2h_bytes_per_step': N * (4 * BEAMS + 4 + 4 + 16) * world_size, 'steps': args.e2e_steps},
+                    'd2h_bytes_per_step': N * (4 * BEAMS + 4 + 4 + 16) * world_size, 'steps': args.e2e_steps,
+                    'how': 'rlca_env_step_host, pinned buffers, library-default world ranges (scans of range k cross '
+                           'PCIe while range k+1 is ticked); every call ends with a stream synchronize',
+                    'serial_value': e2e_serial},
             'e2e_obs_on_device': {'value': e2e_noobs, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': N * 8 * world_size,
                                   'd2h_bytes_per_step': N * (4 + 4 + 16) * world_size,
                                   'note': 'same host-buffer call with the scans left in HBM for an on-device policy'},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
+        if e2e_sweep is not None:
+            line['e2e_sweep_host_chunks'] = e2e_sweep
         if world_size == 1:
             line['learner'] = time_learner(dev, N)
         if world_size == 1 and not args.no_cpu:

@@ -160,7 +160,12 @@ int rlca_env_step(rlca_env *env, const rlca_env_state *state_in, const rlca_env_
 /* Same tick driven from HOST buffers (the reference-facing call: actions arrive from
  * the host, observations/rewards/flags return to it).  H2D of action_host, the tick,
  * D2H of obs/reward/flags/gs, then a stream synchronize.  Any *_host may be NULL to
- * skip that copy.  io holds the device staging buffers. */
+ * skip that copy.  io holds the device staging buffers.  The scans dominate the bytes
+ * (4*beams of 4*beams + 24 per agent) and PCIe is ~100x slower than the tick, so the
+ * shard is ticked in `host chunks` world ranges and each range's scans cross the link
+ * on an internal copy stream while the next range is ticked; results are identical to
+ * the single launch (worlds are independent).  Pinned host buffers are needed for the
+ * overlap (pageable ones still work, staged by the driver). */
 int rlca_env_step_host(rlca_env *env, const rlca_env_state *state_in, const rlca_env_state *state_out,
                        const rlca_step_io *io, const float *action_host, float *obs_host,
                        float *reward_host, uint8_t *flags_host, float *gs_host, void *stream);
@@ -169,6 +174,12 @@ int rlca_env_step_host(rlca_env *env, const rlca_env_state *state_in, const rlca
  * pose_dev (N,4) x,y,theta,_ -> ranges_dev (N,beams) in metres (normalise = 0) or
  * scan/6-0.5 (normalise = 1).  Other robots' footprints are seen, own is excluded. */
 int rlca_raycast(rlca_env *env, const float *pose_dev, float *ranges_dev, int32_t normalise, void *stream);
+
+/* World ranges per rlca_env_step_host call: 0 = library default (2), 1 = strictly serial
+ * (copy in, one launch, copy out), up to 16.  -1 (experimental) = one launch whose lidar
+ * epilogue stores the scans directly into the mapped pinned obs_host (io->obs_dev is then
+ * not written). */
+int rlca_env_set_host_chunks(rlca_env *env, int32_t chunks);
 
 /* Launch shape knob: CTAs per world (>= 1).  0 = library default (auto). */
 int rlca_env_set_ctas_per_world(rlca_env *env, int32_t ctas_per_world);

@@ -120,6 +120,10 @@ class StageWorld:
     def set_ctas_per_world(self, s):
         _lib.check(self.lib.rlca_env_set_ctas_per_world(self._h, int(s)))
 
+    def set_host_chunks(self, k):
+        """World ranges per `step_host` call (0 = library default, 1 = strictly serial)."""
+        _lib.check(self.lib.rlca_env_set_host_chunks(self._h, int(k)))
+
     # ------------------------------------------------------------------ reference surface
     def reset_world(self):
         """reset_positions service + zeroed speeds (stage_world1.py:162-169)."""
@@ -215,9 +219,10 @@ class StageWorld:
                               reward=torch.empty(self.N).pin_memory(),
                               flags=torch.empty(self.N, 4, dtype=torch.uint8).pin_memory(),
                               gs=torch.empty(self.N, 4).pin_memory())
+            # the structs never change between calls: build them once (two ping-pong orientations)
+            self._host_args = [(self._state_struct(k), self._state_struct(1 - k), self._io()) for k in (0, 1)]
         h = self._host
-        s_in, s_out = self._state_struct(self._cur), self._state_struct(1 - self._cur)
-        io = self._io()
+        s_in, s_out, io = self._host_args[self._cur]
         _lib.check(self.lib.rlca_env_step_host(
             self._h, C.byref(s_in), C.byref(s_out), C.byref(io), _ptr(action_host),
             _ptr(h['obs']) if want_obs else C.c_void_p(0), _ptr(h['reward']), _ptr(h['flags']), _ptr(h['gs']),

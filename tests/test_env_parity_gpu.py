@@ -149,8 +149,13 @@ def test_headline_size_properties(built):
     assert np.array_equal(orc.pose.view(np.uint32), pose_big[100 * R:103 * R].view(np.uint32))
 
 
-def test_step_host_matches_device_path(built):
-    sc, env, orc = make_pair('stage1', num_worlds=4, seed=2)
+@pytest.mark.parametrize('scenario,worlds,chunks', [('stage1', 4, 0), ('stage1', 7, 3), ('stage1', 3, 16),
+                                                    ('stage1', 5, 1), ('stage2', 5, 2), ('stage1', 4, -1)])
+def test_step_host_matches_device_path(built, scenario, worlds, chunks):
+    """The host-buffer call, serial (1) and pipelined over world ranges (uneven ranges, more chunks than worlds,
+    the stage-2 group barrier inside a range): bit-identical to the oracle, i.e. to the single launch."""
+    sc, env, orc = make_pair(scenario, num_worlds=worlds, seed=2, auto_reset=2 if scenario == 'stage2' else True)
+    env.set_host_chunks(chunks)
     env.reset_pose()
     orc.reset_world()
     orc.reset_pose()
@@ -164,6 +169,24 @@ def test_step_host_matches_device_path(built):
         assert np.array_equal(h['obs'].numpy().view(np.uint32), orc.obs.view(np.uint32))
         assert np.array_equal(h['reward'].numpy().view(np.uint32), orc.reward.view(np.uint32))
         assert np.array_equal(h['flags'].numpy(), orc.flags)
+        assert np.array_equal(h['gs'].numpy().view(np.uint32), orc.gs.view(np.uint32))
+    assert_state_equal(env, orc, f'step_host chunks={chunks}')
+
+
+def test_wide_register_tick_kernel_is_bit_identical(built, monkeypatch):
+    """RLCA_WIDE=1 selects the 48-register (5 CTAs/SM) build of the tick kernel: same results."""
+    monkeypatch.setenv('RLCA_WIDE', '1')
+    sc, env, orc = make_pair('stage1', num_worlds=6, seed=11)
+    env.reset_pose()
+    orc.reset_world()
+    orc.reset_pose()
+    rng = np.random.default_rng(5)
+    for t in range(30):
+        a = random_actions(rng, orc.N, wide=True)
+        env.control_vel(torch.from_numpy(a).cuda())
+        orc.step(a)
+        assert_outputs_equal(env, orc, f'wide t={t}')
+    assert_state_equal(env, orc, 'wide')
 
 
 def test_errors_are_loud(built):

@@ -142,3 +142,52 @@ def test_robot_robot_collision_reverts_and_stalls():
             assert np.all(w.reward[hit] <= -14.0)
             break
     assert crashed_at is not None
+
+
+def test_fp32_tick_tracks_double_precision_stage_arithmetic():
+    """Deviation D4: Stage integrates in double (x += v dt cos th, y += v dt sin th,
+    th = normalize(th + w dt), old heading used for the translation) and the Python client computes reward and local
+    goal in float64 (stage_world1.py:155-160,180-211).  The oracle's fp32 contract must stay within the north-star's
+    1e-4 of that arithmetic over a whole stage-1 episode (150 ticks) of random commands."""
+    rng = np.random.default_rng(42)
+    R = 8
+    init = np.column_stack([rng.uniform(-8, 8, R), rng.uniform(-8, 8, R), rng.uniform(-math.pi, math.pi, R)])
+    goals = np.column_stack([rng.uniform(25, 30, R), rng.uniform(25, 30, R)])      # never reached
+    init[:, :2] += np.arange(R)[:, None] * 40.0            # far apart: no robot-robot contact
+    goals += np.arange(R)[:, None] * 40.0
+    sc, w = empty_world(R=R, cells=3200, init=init, goals=goals, timeout=10000, w_threshold=0.7)
+    w.reset_world()
+    w.reset_pose()
+    x = w.pose[:, 0].astype(np.float64)
+    y = w.pose[:, 1].astype(np.float64)
+    th = w.pose[:, 2].astype(np.float64)
+    gx, gy = w.goal[:, 0].astype(np.float64), w.goal[:, 1].astype(np.float64)
+    d_prev = np.hypot(gx - x, gy - y)                       # pre_distance = true distance (stage_world1.py:174-177)
+    worst = dict(pos=0.0, pos0=0.0, th=0.0, rew=0.0, lg=0.0)
+    for t in range(150):
+        a = np.column_stack([rng.uniform(0, 1, R), rng.uniform(-1, 1, R)]).astype(np.float32)
+        w.step(a)
+        v, om = a[:, 0].astype(np.float64), a[:, 1].astype(np.float64)
+        th_old = th.copy()
+        x = x + v * 0.1 * np.cos(th)
+        y = y + v * 0.1 * np.sin(th)
+        th = th + om * 0.1
+        th = np.where(th > math.pi, th - 2 * math.pi, np.where(th <= -math.pi, th + 2 * math.pi, th))
+        w_gt = (np.mod(th - th_old + math.pi, 2 * math.pi) - math.pi) / 0.1       # stageros.cpp:581-593
+        d = np.hypot(gx - x, gy - y)
+        rew = 2.5 * (d_prev - d) + np.where(np.abs(w_gt) > 0.7, -0.1 * np.abs(w_gt), 0.0)
+        d_prev = d
+        lgx = (gx - x) * np.cos(th) + (gy - y) * np.sin(th)                         # stage_world1.py:155-160
+        lgy = -(gx - x) * np.sin(th) + (gy - y) * np.cos(th)
+        worst['pos'] = max(worst['pos'], np.abs(w.pose[:, 0] - x).max(), np.abs(w.pose[:, 1] - y).max())
+        worst['pos0'] = max(worst['pos0'], abs(w.pose[0, 0] - x[0]), abs(w.pose[0, 1] - y[0]))
+        worst['th'] = max(worst['th'], np.abs(w.pose[:, 2] - th).max())
+        # |w_gt| near the 0.7 threshold may flip the penalty term between fp32 and double: compare away from it
+        clear = np.abs(np.abs(w_gt) - 0.7) > 1e-4
+        worst['rew'] = max(worst['rew'], np.abs(w.reward - rew)[clear].max() if clear.any() else 0.0)
+        worst['lg'] = max(worst['lg'], np.abs(w.gs[:, 0] - lgx).max(), np.abs(w.gs[:, 1] - lgy).max())
+    assert not w.flags[:, 0].any()
+    # robot 0 moves at arena-scale coordinates (|x| < 25 m): the north-star's 1e-4.  The others sit up to 300 m out
+    # (40 m apart so that nobody touches), where one fp32 ulp is already 3e-5: 1e-3.
+    assert worst['pos0'] < 1e-4 and worst['th'] < 1e-4, worst
+    assert worst['pos'] < 1e-3 and worst['rew'] < 2e-3 and worst['lg'] < 2e-3, worst
