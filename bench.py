@@ -8,8 +8,8 @@ raycast + reward/done + obs) over the per-GPU agent batch: 171 stage-1 worlds x 
 data-path collective (worlds are independent).
 
   value        whole-job agent-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e          same metric through the host-buffer C-ABI call (pinned action H2D, tick in world
-               ranges with the scans' D2H overlapped, reward/flags/gs D2H, sync) — the reference-facing call
+  e2e          same metric through the host-buffer C-ABI call (actions read from and obs/reward/flags/gs
+               written to pinned host memory over PCIe by the tick kernel itself, sync) — the reference-facing call
   roofline     algorithmic bytes (4*B+96 per agent-step) / measured launch time
                vs the measured HBM copy peak (MEASURED_PEAKS.json, else the 6650 GB/s fallback)
   cpu_baseline the CPU oracle (port of the reference semantics) on the host cores, bounded sample
@@ -297,8 +297,9 @@ def main():
     # ---- e2e: the host-buffer call (pinned action H2D, tick, obs/reward/flags/gs D2H, sync inside every call)
     a_host = [torch.from_numpy(random_actions(rng, N)).pin_memory() for _ in range(8)]
 
-    def time_e2e(want_obs=True, chunks=0):
+    def time_e2e(want_obs=True, chunks=0, mode=1):
         env.set_host_chunks(chunks)
+        env.set_host_zero_copy(mode)
         for i in range(5):
             env.step_host(a_host[i % 8], want_obs=want_obs)
         sync()
@@ -310,16 +311,17 @@ def main():
         if world_size > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         env.set_host_chunks(0)
+        env.set_host_zero_copy(1)
         return N * world_size * args.e2e_steps / float(te.item())
 
-    e2e_val = time_e2e()                         # library default: ticked in world ranges, scans overlap the next range
-    e2e_serial = time_e2e(chunks=1)              # copy in, one launch, copy out (the round-1 number, for comparison)
+    e2e_val = time_e2e()                         # library default: no DMA, the kernel reads/writes pinned host memory
+    e2e_serial = time_e2e(chunks=1, mode=0)      # copy in, one launch, copy out (the earlier round-1 number, for comparison)
     # variant for callers that keep the policy on the device: same call, but the observations stay in HBM
     # (action H2D + tick + reward/flags/goal-speed D2H + sync).  Reported next to `e2e`, never instead of it.
     e2e_noobs = time_e2e(want_obs=False)
     e2e_sweep = None
     if args.e2e_sweep:
-        e2e_sweep = {str(k): time_e2e(chunks=k) for k in (1, 2, 3, 4, 6, 8, 12, 16, -1)}
+        e2e_sweep = {f'mode{m}_chunks{k}': time_e2e(chunks=k, mode=m) for m in (0, 2) for k in (1, 2, 3, 4, 8)}
 
     if rank == 0:
         value = N * world_size * args.steps / (ms_max * 1e-3)
@@ -351,8 +353,9 @@ def main():
                          'note': 'per-GPU; the march is issue/shared-memory bound, not HBM bound (DESIGN.md §6)'},
             'e2e': {'value': e2e_val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': N * 8 * world_size,
                     'd2h_bytes_per_step': N * (4 * BEAMS + 4 + 4 + 16) * world_size, 'steps': args.e2e_steps,
-                    'how': 'rlca_env_step_host, pinned buffers, library-default world ranges (scans of range k cross '
-                           'PCIe while range k+1 is ticked); every call ends with a stream synchronize',
+                    'how': 'rlca_env_step_host with pinned host buffers, library default: the tick kernel reads the '
+                           'actions from host memory and mirrors obs/reward/flags/gs to it over PCIe while it runs (no '
+                           'DMA operations); every call ends with a stream synchronize',
                     'serial_value': e2e_serial},
             'e2e_obs_on_device': {'value': e2e_noobs, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': N * 8 * world_size,
                                   'd2h_bytes_per_step': N * (4 + 4 + 16) * world_size,

@@ -158,14 +158,21 @@ int rlca_env_step(rlca_env *env, const rlca_env_state *state_in, const rlca_env_
                   const rlca_step_io *io, void *stream);
 
 /* Same tick driven from HOST buffers (the reference-facing call: actions arrive from
- * the host, observations/rewards/flags return to it).  H2D of action_host, the tick,
- * D2H of obs/reward/flags/gs, then a stream synchronize.  Any *_host may be NULL to
- * skip that copy.  io holds the device staging buffers.  The scans dominate the bytes
- * (4*beams of 4*beams + 24 per agent) and PCIe is ~100x slower than the tick, so the
- * shard is ticked in `host chunks` world ranges and each range's scans cross the link
- * on an internal copy stream while the next range is ticked; results are identical to
- * the single launch (worlds are independent).  Pinned host buffers are needed for the
- * overlap (pageable ones still work, staged by the driver). */
+ * the host, observations/rewards/flags return to it), ending with a stream synchronize.
+ * Any *_host may be NULL to skip it.  io holds the device buffers, which are written as
+ * by rlca_env_step (except action_dev in the zero-copy modes).  Host traffic, see
+ * rlca_env_set_host_zero_copy:
+ *   1 (default) pinned host buffers are used through their device-mapped aliases: the
+ *               kernel reads action_host and mirrors reward/flags/gs and every scan to
+ *               host memory with posted PCIe writes while it runs - no DMA operation at
+ *               all in the call;
+ *   2           the same for the small buffers, the scans (4*beams of the 4*beams + 24
+ *               bytes an agent returns) cross by DMA: the shard is ticked in `host chunks`
+ *               world ranges and each range's scans are copied on an internal stream
+ *               while the next range is ticked;
+ *   0           DMA copies only (H2D, tick in world ranges, D2H).
+ * Pageable host buffers and the global-grid path fall back to mode 0.  Results are
+ * identical in every mode (worlds are independent). */
 int rlca_env_step_host(rlca_env *env, const rlca_env_state *state_in, const rlca_env_state *state_out,
                        const rlca_step_io *io, const float *action_host, float *obs_host,
                        float *reward_host, uint8_t *flags_host, float *gs_host, void *stream);
@@ -175,11 +182,11 @@ int rlca_env_step_host(rlca_env *env, const rlca_env_state *state_in, const rlca
  * scan/6-0.5 (normalise = 1).  Other robots' footprints are seen, own is excluded. */
 int rlca_raycast(rlca_env *env, const float *pose_dev, float *ranges_dev, int32_t normalise, void *stream);
 
-/* World ranges per rlca_env_step_host call: 0 = library default (2), 1 = strictly serial
- * (copy in, one launch, copy out), up to 16.  -1 (experimental) = one launch whose lidar
- * epilogue stores the scans directly into the mapped pinned obs_host (io->obs_dev is then
- * not written). */
+/* World ranges per rlca_env_step_host call on the DMA path: 0 = library default (2),
+ * 1 = strictly serial (copy in, one launch, copy out), up to 16. */
 int rlca_env_set_host_chunks(rlca_env *env, int32_t chunks);
+/* Host traffic mode of rlca_env_step_host: 0, 1 or 2 (see there). */
+int rlca_env_set_host_zero_copy(rlca_env *env, int32_t mode);
 
 /* Launch shape knob: CTAs per world (>= 1).  0 = library default (auto). */
 int rlca_env_set_ctas_per_world(rlca_env *env, int32_t ctas_per_world);

@@ -66,6 +66,7 @@ SYMBOLS = {
     'rlca_raycast': (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     'rlca_env_set_ctas_per_world': (C.c_int, [_P, C.c_int32]),
     'rlca_env_set_host_chunks': (C.c_int, [_P, C.c_int32]),
+    'rlca_env_set_host_zero_copy': (C.c_int, [_P, C.c_int32]),
     'rlca_env_launch_count': (C.c_int64, [_P]),
     'rlca_sizeof_env_config': (C.c_int, []),
     'rlca_policy_param_offset': (C.c_int64, [C.c_int32]),

@@ -124,6 +124,11 @@ class StageWorld:
         """World ranges per `step_host` call (0 = library default, 1 = strictly serial)."""
         _lib.check(self.lib.rlca_env_set_host_chunks(self._h, int(k)))
 
+    def set_host_zero_copy(self, mode):
+        """`step_host` host traffic: 1 = the kernel reads actions from / mirrors all outputs to pinned host memory (no
+        DMA), 2 = small buffers only (scans by DMA in world ranges), 0 = DMA copies."""
+        _lib.check(self.lib.rlca_env_set_host_zero_copy(self._h, int(mode)))
+
     # ------------------------------------------------------------------ reference surface
     def reset_world(self):
         """reset_positions service + zeroed speeds (stage_world1.py:162-169)."""
@@ -213,7 +218,7 @@ class StageWorld:
 
     def step_host(self, action_host, want_obs=True):
         """Reference-facing tick with HOST buffers: pinned action in, pinned obs/reward/flags/gs
-        out, copies and a stream sync inside the call (rlca_env_step_host)."""
+        out, host<->device traffic and a stream sync inside the call (rlca_env_step_host)."""
         if self._host is None:
             self._host = dict(obs=torch.empty(self.N, self.beam_mum).pin_memory(),
                               reward=torch.empty(self.N).pin_memory(),

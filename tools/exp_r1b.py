@@ -31,10 +31,10 @@ WORLDS, BEAMS = 171, 512
 dev = torch.device('cuda', 0)
 
 
-def make_env(wide, ctas):
+def make_env(wide, ctas, worlds=WORLDS, scenario='stage1'):
     os.environ['RLCA_WIDE'] = str(wide)
-    env = StageWorld(BEAMS, index=0, scenario='stage1', num_worlds=WORLDS, device=dev, seed=0, auto_reset=True,
-                     ctas_per_world=ctas)
+    env = StageWorld(BEAMS, index=0, scenario=scenario, num_worlds=worlds, device=dev, seed=0,
+                     auto_reset=2 if scenario == 'stage2' else True, ctas_per_world=ctas)
     env.reset_pose()
     return env
 
@@ -59,27 +59,54 @@ def main():
     ring = torch.empty(128, N, BEAMS, device=dev)
     for rep in range(2):                       # two passes: the second one shows the run-to-run spread
         for wide in (0, 1):
-            for ctas in (0, 3, 4, 6, 8):
+            for ctas in (0, 4):
                 env = make_env(wide, ctas)
                 us = time_ticks(env, acts, ring)
                 print(json.dumps({'exp': 'tick', 'rep': rep, 'wide': wide, 'ctas_per_world': ctas, 'us_per_tick': us,
                                   'agent_steps_per_s': N / us * 1e6}), flush=True)
                 env.close()
-    env = make_env(0, 0)
+    # other batch sizes / scenario: which register build wins when more than 5 CTAs per SM could be resident?
+    for rep in range(2):
+        for scenario, worlds, R in (('stage1', 43, 24), ('stage1', 684, 24), ('stage1', 2731, 24), ('stage2', 94, 44)):
+            n = worlds * R
+            a2 = [torch.from_numpy(random_actions(rng, n)).to(dev) for _ in range(64)]
+            r2 = torch.empty(128 if n < 20000 else 16, n, BEAMS, device=dev)
+            for wide in (0, 1, 2):
+                env = make_env(wide, 0, worlds, scenario)
+                for i in range(20):
+                    env.control_vel(a2[i % 64], obs_out=r2[i % r2.shape[0]])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(200):
+                    env.control_vel(a2[i % 64], obs_out=r2[i % r2.shape[0]])
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) / 200 * 1e3
+                print(json.dumps({'exp': 'tick_sizes', 'rep': rep, 'scenario': scenario, 'robots': n, 'wide': wide,
+                                  'us_per_tick': us, 'agent_steps_per_s': n / us * 1e6}), flush=True)
+                env.close()
+            del a2, r2
+    env = make_env(1, 0)
     a_host = [torch.from_numpy(random_actions(rng, N)).pin_memory() for _ in range(8)]
     for rep in range(2):
-        for k in (1, 2, 3, 4, 6, 8, 12, 16, -1):
-            env.set_host_chunks(k)
-            for i in range(10):
-                env.step_host(a_host[i % 8])
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for i in range(300):
-                env.step_host(a_host[i % 8])
-            torch.cuda.synchronize()
-            us = (time.perf_counter() - t0) / 300 * 1e6
-            print(json.dumps({'exp': 'e2e', 'rep': rep, 'host_chunks': k, 'us_per_step': us,
-                              'agent_steps_per_s': N / us * 1e6}), flush=True)
+        for zc in (0, 2, 1):
+            env.set_host_zero_copy(zc)
+            for k in ((1, 2, 3) if zc != 1 else (1,)):
+                env.set_host_chunks(k)
+                for want_obs in (True, False):
+                    if not want_obs and k != 1:
+                        continue
+                    for i in range(10):
+                        env.step_host(a_host[i % 8], want_obs=want_obs)
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for i in range(300):
+                        env.step_host(a_host[i % 8], want_obs=want_obs)
+                    torch.cuda.synchronize()
+                    us = (time.perf_counter() - t0) / 300 * 1e6
+                    print(json.dumps({'exp': 'e2e', 'rep': rep, 'zero_copy': zc, 'host_chunks': k, 'want_obs': want_obs,
+                                      'us_per_step': us, 'agent_steps_per_s': N / us * 1e6}), flush=True)
 
 
 if __name__ == '__main__':
