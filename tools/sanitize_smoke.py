@@ -12,15 +12,23 @@ from rl_collision_avoidance_b200.stage_world import StageWorld
 
 
 def main():
-    for scen, ar in (('stage1', 1), ('stage2', 2)):
-        env = StageWorld(512, scenario=scen, num_worlds=2, seed=1, auto_reset=ar)
+    for scen, ar, beams in (('stage1', 1, 512), ('stage2', 2, 512), ('stage1', 1, 180)):
+        env = StageWorld(beams, scenario=scen, num_worlds=2, seed=1, auto_reset=ar)
         env.reset_pose()
-        st = [env.obs[:, None, :].repeat(1, 3, 1).contiguous(), torch.empty(env.N, 3, 512, device='cuda')]
+        st = [env.obs[:, None, :].repeat(1, 3, 1).contiguous(), torch.empty(env.N, 3, beams, device='cuda')]
         for t in range(6):
             env.control_vel(torch.rand(env.N, 2, device='cuda'), stack_in=st[t % 2], stack_out=st[(t + 1) % 2])
         env.raycast(env.state['pose'].clone())
+        # the host-buffer call in its three traffic modes (kernel-written pinned host memory, mixed, DMA in world ranges)
+        a_host = torch.rand(env.N, 2).pin_memory()
+        for mode in (1, 2, 0):
+            env.set_host_zero_copy(mode)
+            env.step_host(a_host)
         torch.cuda.synchronize()
         env.close()
+    if '--env-only' in sys.argv:
+        print('sanitize workload done (env only)')
+        return
     if '--circle' in sys.argv:
         env = StageWorld(512, scenario='circle', num_worlds=1, seed=1, auto_reset=1)
         env.reset_pose()
