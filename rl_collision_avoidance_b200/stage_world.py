@@ -81,12 +81,17 @@ class StageWorld:
         self.eplog = torch.zeros(N, 8, device=dev)
         self._action = torch.zeros(N, 2, device=dev)
         self._host = None
+        self._host_ptrs = None
         self.reset_world()
 
     # ------------------------------------------------------------------ plumbing
     def _state_struct(self, k):
-        s = self._st[k]
-        return _lib.EnvState(_ptr(s['pose']), _ptr(s['goal']), _ptr(s['acc']), _ptr(s['meta']))
+        # the ping-pong state tensors never move: build each struct once
+        cache = self.__dict__.setdefault('_state_structs', {})
+        if k not in cache:
+            s = self._st[k]
+            cache[k] = _lib.EnvState(_ptr(s['pose']), _ptr(s['goal']), _ptr(s['acc']), _ptr(s['meta']))
+        return cache[k]
 
     def _io(self, action=None, live=None, obs=None, stack_in=None, stack_out=None, out=None):
         o = out or {}
@@ -227,11 +232,13 @@ class StageWorld:
             # the structs never change between calls: build them once (two ping-pong orientations)
             self._host_args = [(self._state_struct(k), self._state_struct(1 - k), self._io()) for k in (0, 1)]
         h = self._host
+        if self._host_ptrs is None or self._host_ptrs[0] is not h:
+            self._host_ptrs = (h, _ptr(h['obs']), _ptr(h['reward']), _ptr(h['flags']), _ptr(h['gs']), C.c_void_p(0))
+        _, p_obs, p_rew, p_flg, p_gs, p_null = self._host_ptrs
         s_in, s_out, io = self._host_args[self._cur]
         _lib.check(self.lib.rlca_env_step_host(
             self._h, C.byref(s_in), C.byref(s_out), C.byref(io), _ptr(action_host),
-            _ptr(h['obs']) if want_obs else C.c_void_p(0), _ptr(h['reward']), _ptr(h['flags']), _ptr(h['gs']),
-            self._stream()))
+            p_obs if want_obs else p_null, p_rew, p_flg, p_gs, self._stream()))
         self._cur = 1 - self._cur
         return h
 
