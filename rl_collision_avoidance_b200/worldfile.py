@@ -103,10 +103,21 @@ def _instantiate(name, macros) -> Entity:
     return ent
 
 
+class WorldFileError(ValueError):
+    """Malformed world file (unbalanced brackets, bad define, geometry that cannot be rasterised)."""
+
+
 def parse_worldfile(path: str):
-    """Returns (globals dict, list of top-level entities)."""
+    """Returns (globals dict, list of top-level entities).  Raises WorldFileError on malformed input."""
     with open(path, 'r') as f:
         toks = _tokenize(f.read())
+    try:
+        return _parse_tokens(toks)
+    except IndexError:
+        raise WorldFileError(f"{path}: unexpected end of file (unbalanced '(' or '[')") from None
+
+
+def _parse_tokens(toks):
     macros = {}
     globals_ = {}
     entities = []
@@ -115,7 +126,8 @@ def parse_worldfile(path: str):
         t = toks[i]
         if t == 'define':
             name, base = toks[i + 1], toks[i + 2]
-            assert toks[i + 3] == '(', f'bad define near token {i}'
+            if toks[i + 3] != '(':
+                raise WorldFileError(f"define {name}: expected '(' after the base model, got {toks[i + 3]!r}")
             ent = _instantiate(base, macros)
             ent.kind = name
             i = _parse_body(toks, i + 4, ent, macros)
@@ -249,6 +261,8 @@ def load_world(path: str, pitch_align: int = 16, margin: int = 1) -> WorldMap:
             if img.ndim == 3:
                 img = img[:, :, 0]
             rects = bitmap_rects(img)
+            if not rects or size is None:
+                raise WorldFileError(f'{path}: bitmap model {ent.get("name", ent.kind)!r} needs dark pixels and a size')
             xs0 = min(r[0] for r in rects)
             ys0 = min(r[1] for r in rects)
             xs1 = max(r[0] + r[2] for r in rects)
@@ -258,6 +272,8 @@ def load_world(path: str, pitch_align: int = 16, margin: int = 1) -> WorldMap:
                 bw, bh = xs1 - xs0, ys1 - ys0
                 rects = rects + [(xs0, ys0, eps, bh), (xs0, ys0, bw, eps),
                                  (xs0, ys1 - eps, bw, eps), (xs1 - eps, ys0, eps, bh)]
+            if xs1 <= xs0 or ys1 <= ys0:
+                raise WorldFileError(f'{path}: bitmap {ent.get("bitmap")!r} has a degenerate obstacle extent')
             scx = float(size[0]) / (xs1 - xs0)
             scy = float(size[1]) / (ys1 - ys0)
             offx, offy = 0.5 * (xs0 + xs1), 0.5 * (ys0 + ys1)
@@ -288,12 +304,16 @@ def load_world(path: str, pitch_align: int = 16, margin: int = 1) -> WorldMap:
                 continue
             minx, maxx = min(p[0] for p in allp), max(p[0] for p in allp)
             miny, maxy = min(p[1] for p in allp), max(p[1] for p in allp)
+            if maxx <= minx or maxy <= miny:
+                raise WorldFileError(f'{path}: obstacle at {ent.get("pose")} has a degenerate polygon')
             scx = float(size[0]) / (maxx - minx)
             scy = float(size[1]) / (maxy - miny)
             offx, offy = 0.5 * (minx + maxx), 0.5 * (miny + maxy)
             for poly in polys:
                 loc = [((px - offx) * scx, (py - offy) * scy) for px, py in poly]
                 marked.update(_polygon_cells(_transform(loc, pose), ppm))
+    if not marked:
+        raise WorldFileError(f'{path}: no static geometry (floorplan bitmap or polygon obstacle) found')
     xs = [c[0] for c in marked]
     ys = [c[1] for c in marked]
     minx, maxx, miny, maxy = min(xs), max(xs), min(ys), max(ys)

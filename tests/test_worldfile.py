@@ -1,7 +1,9 @@
 """World-file + bitmap loader on a tiny synthetic world (no reference files needed)."""
 import numpy as np
 
-from rl_collision_avoidance_b200.worldfile import bitmap_rects, load_world, parse_worldfile
+import pytest
+
+from rl_collision_avoidance_b200.worldfile import WorldFileError, bitmap_rects, load_world, parse_worldfile
 
 WORLD = '''
 # comment
@@ -59,3 +61,33 @@ def test_load_world(tmp_path):
     assert not cell(-2.0, 0.9) and not cell(2.9, -1.0)                                    # free interior
     assert cell(2.0, 1.0) or cell(1.6, 0.6)                                               # polygon obstacle outline
     assert m.cells.shape[1] % 4 == 0
+
+
+@pytest.mark.parametrize('text,what', [
+    ('resolution 0.5\nbot( pose [1 2 0 90]', 'unbalanced'),                 # missing ')'
+    ('resolution 0.5\nbot( pose [1 2 0 90 )', 'unbalanced'),                # missing ']' swallows the rest
+    ('define bot position size [1 1 1] )', "expected '('"),                 # define without a body
+])
+def test_malformed_world_files_raise_a_clear_error(tmp_path, text, what):
+    f = tmp_path / 'bad.world'
+    f.write_text(text)
+    with pytest.raises(WorldFileError, match=what.replace('(', r'\(')):
+        parse_worldfile(str(f))
+
+
+def test_world_without_static_geometry_is_rejected(tmp_path):
+    f = tmp_path / 'empty.world'
+    f.write_text('resolution 0.2\ndefine laser ranger ( )\ndefine bot position ( laser( ) )\nbot( pose [0 0 0 0] )\n')
+    with pytest.raises(WorldFileError, match='no static geometry'):
+        load_world(str(f))
+
+
+def test_degenerate_polygon_obstacle_is_rejected(tmp_path):
+    from PIL import Image
+    Image.fromarray(np.zeros((4, 4), np.uint8), 'L').save(tmp_path / 'm.png')
+    f = tmp_path / 'deg.world'
+    f.write_text('resolution 0.5\ndefine wall model ( )\nwall( size [2 2 1] pose [0 0 0 0] bitmap "m.png" )\n'
+                 'define obstacle position ( )\n'
+                 'obstacle( pose [0 0 0 0] size [1 1 1] block( points 2 point[0] [0 0] point[1] [1 0] ) )\n')
+    with pytest.raises(WorldFileError, match='degenerate polygon'):
+        load_world(str(f))
