@@ -137,8 +137,11 @@ int rlca_env_set_map(rlca_env *env, const uint8_t *cells_host, int32_t grid_w, i
 int rlca_env_set_tables(rlca_env *env, const float *init_tab_host, const float *goal_tab_host);
 
 /* reset_world (stage_world1.py:162-169 -> cb_reset_srv stageros.cpp:260-269) when
- * clear_world != 0, then reset_pose + generate_goal_point (stage_world1.py:171-177,213-223)
- * for agents with mask != 0 (mask_dev NULL = all agents).  In place. */
+ * clear_world == 1, then reset_pose + generate_goal_point (stage_world1.py:171-177,213-223)
+ * for agents with mask != 0 (mask_dev NULL = all agents).  In place.
+ * clear_world == 2: generate_goal_point ALONE for the masked agents (stage_world1.py:171-177 ->
+ * generate_random_goal :262-274): a goal for the CURRENT pose from the draws of the current episode,
+ * pre_distance / init_pose refreshed, pose and counters untouched. */
 int rlca_env_reset(rlca_env *env, const rlca_env_state *state, const uint8_t *mask_dev,
                    int32_t clear_world, void *stream);
 
@@ -255,6 +258,16 @@ int rlca_ppo_loss_fwd_bwd(rlca_policy *pol, const float *params_dev, const float
                           const float *action_dev, const float *old_logprob_dev, const float *adv_dev,
                           const float *target_dev, int32_t nb, float clip_value, float coeff_entropy,
                           float value_coef, float *losses_dev, void *stream);
+
+/* Same, with every gradient multiplied by grad_weight (the logged losses are not).  Data-parallel training: a rank
+ * whose minibatch holds nb_r of the step's sum(nb_r) rows passes grad_weight = nb_r * world_size / sum(nb_r), so that
+ * the all-reduced gradient / world_size is the mean over ALL rows of the global minibatch (the reference's single
+ * process sees one batch, model/ppo.py:172-188). */
+int rlca_ppo_loss_fwd_bwd_weighted(rlca_policy *pol, const float *params_dev, const float *value_dev,
+                                   const float *mean_dev, const float *action_dev, const float *old_logprob_dev,
+                                   const float *adv_dev, const float *target_dev, int32_t nb, float clip_value,
+                                   float coeff_entropy, float value_coef, float grad_weight, float *losses_dev,
+                                   void *stream);
 
 /* Backward of the whole network for the batch of the last rlca_policy_forward: writes the
  * flat gradient buffer (RLCA_POLICY_NPARAMS floats; overwritten, not accumulated). */

@@ -94,6 +94,12 @@ class OracleWorld:
                            _p(self.pose), _p(self.goal), _p(self.acc), _p(self.meta))
         self.observe()
 
+    def generate_goal_point(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        self.lib.orc_reset(C.byref(self.cfg), _p(self.init_tab), _p(self.goal_tab), _p(m), 2,
+                           _p(self.pose), _p(self.goal), _p(self.acc), _p(self.meta))
+        self.observe()
+
     def observe(self):
         self.lib.orc_observe(C.byref(self.cfg), _p(self.static), _p(self.pose), _p(self.goal), _p(self.obs), _p(self.gs))
 

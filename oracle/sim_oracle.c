@@ -342,16 +342,20 @@ static void stage2_random_xy(const orc_config *cfg, uint32_t agent, uint32_t epi
 
 /* state arrays are (N,4): pose = x,y,theta,dist ; goal = gx,gy,v_cmd,w_cmd ;
  * acc = ep_reward,last_reward,init_x,init_y ; meta(int32) = t,episode,stall,terminal */
+/* goal_only: generate_goal_point alone (stage_world1.py:171-177) - a new goal for the CURRENT pose with the draws of
+ * the current episode, pre_distance and init_pose refreshed, counters untouched. */
 static void reset_agent(const orc_config *cfg, const float *init_tab, const float *goal_tab,
                         uint32_t agent_gid, int r, float *pose, float *goal, float *acc,
-                        int32_t *meta)
+                        int32_t *meta, int goal_only)
 {
-    uint32_t episode = (uint32_t)(meta[1] + 1);
+    uint32_t episode = (uint32_t)(meta[1] + (goal_only ? 0 : 1));
     meta[1] = (int32_t)episode;
     float u[4];
     float x, y, th;
     int random_pose = (cfg->scenario == 0) || (cfg->scenario == 1 && init_tab[4 * r + 3] != 0.0f);
-    if (cfg->scenario == 0) {
+    if (goal_only) {
+        x = pose[0]; y = pose[1]; th = pose[2];
+    } else if (cfg->scenario == 0) {
         x = y = 0.f;
         for (int k = 0; k < cfg->max_reject; ++k) {
             orc_rand4(cfg->seed, agent_gid, episode, (uint32_t)k, 1u, u);
@@ -393,15 +397,17 @@ static void reset_agent(const orc_config *cfg, const float *init_tab, const floa
     float ddx = gx - x, ddy = gy - y;
     float d0 = sqrtf(fmaf(ddx, ddx, ddy * ddy));
     pose[3] = cfg->pre_distance_zero ? 0.0f : d0;
-    acc[0] = 0.0f;           /* ep_reward */
     acc[2] = x; acc[3] = y;  /* init_pose for the 'Distance' log column (ppo_stage1.py:127) */
+    if (goal_only) return;
+    acc[0] = 0.0f;           /* ep_reward */
     meta[0] = 1;             /* step = 1 (ppo_stage1.py:57) */
     meta[3] = 0;             /* terminal latch cleared */
 }
 
 /* reset_world (stage_world1.py:162-169 -> cb_reset_srv stageros.cpp:260-269):
  * world-file poses restored, stall cleared, speeds zeroed.  Then optional per-agent
- * reset_pose + generate_goal_point for agents with mask != 0 (mask NULL = all). */
+ * reset_pose + generate_goal_point for agents with mask != 0 (mask NULL = all).
+ * clear_world == 2: generate_goal_point only (new goal for the current pose). */
 void orc_reset(const orc_config *cfg, const float *init_tab, const float *goal_tab,
                const uint8_t *mask, int clear_world,
                float *pose, float *goal, float *acc, int32_t *meta)
@@ -411,7 +417,7 @@ void orc_reset(const orc_config *cfg, const float *init_tab, const float *goal_t
     for (int i = 0; i < N; ++i) {
         int r = i % R;
         uint32_t gid = (uint32_t)(cfg->world_offset * R + i);
-        if (clear_world) {
+        if (clear_world == 1) {
             pose[4 * i + 0] = init_tab[4 * r + 0];
             pose[4 * i + 1] = init_tab[4 * r + 1];
             pose[4 * i + 2] = orc_normalize(init_tab[4 * r + 2]);
@@ -423,7 +429,7 @@ void orc_reset(const orc_config *cfg, const float *init_tab, const float *goal_t
         }
         if (mask == NULL || mask[i])
             reset_agent(cfg, init_tab, goal_tab, gid, r, pose + 4 * i, goal + 4 * i, acc + 4 * i,
-                        meta + 4 * i);
+                        meta + 4 * i, clear_world == 2);
     }
 }
 
@@ -555,7 +561,7 @@ void orc_step(const orc_config *cfg, const uint8_t *static_cells,
                 }
                 if (do_reset) {
                     uint32_t gid = (uint32_t)((cfg->world_offset + w) * R + r);
-                    reset_agent(cfg, init_tab, goal_tab, gid, r, pose + 4 * i, goal + 4 * i, acc + 4 * i, meta + 4 * i);
+                    reset_agent(cfg, init_tab, goal_tab, gid, r, pose + 4 * i, goal + 4 * i, acc + 4 * i, meta + 4 * i, 0);
                     nx[r] = pose[4 * i + 0]; ny[r] = pose[4 * i + 1]; nth[r] = pose[4 * i + 2];
                     flags[4 * i + 3] = 1;
                     rebuild = 1;

@@ -94,6 +94,7 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
         logger.info('#####################################')
         logger.info('############Start Training###########')
         logger.info('#####################################')
+    start_update = 0
     if args.resume:
         policy.load_state_dict(torch.load(args.resume, map_location=device))
         extra = args.resume + '.trainer'
@@ -101,6 +102,7 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
             st = torch.load(extra, map_location=device)
             opt.load_state_dict(st['optimizer'])
             policy.sample_counter = int(st.get('sample_counter', 0))
+            start_update = int(st.get('update', 0))              # checkpoint names continue instead of overwriting
             if logger:
                 logger.info('resumed from %s (update %d, Adam step %d)' % (args.resume, st.get('update', -1), opt.step_count))
     hp = dict(HORIZON=HORIZON, GAMMA=GAMMA, LAMDA=LAMDA, BATCH_SIZE=batch_size, EPOCH=epoch, COEFF_ENTROPY=COEFF_ENTROPY,
@@ -108,7 +110,8 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
               MAX_EPISODES=MAX_EPISODES)
     try:
         stats = run(env=env, policy=policy, policy_path=args.policy_path, action_bound=action_bound, optimizer=opt, hp=hp,
-                    logger=logger, logger_cal=logger_cal, stage=stage, max_updates=args.updates, process_group=pg, rank=rank)
+                    logger=logger, logger_cal=logger_cal, stage=stage, max_updates=args.updates, process_group=pg, rank=rank,
+                    start_update=start_update)
         if rank == 0 and stats:
             s = stats[-1]
             print('update %d: rollout %.3fs update %.3fs -> %.0f agent-steps/s per GPU; mean ep reward %.2f' %

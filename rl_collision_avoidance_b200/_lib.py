@@ -81,6 +81,8 @@ SYMBOLS = {
     'rlca_policy_sample': (C.c_int, [_P, _P, C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, _P, _P, _P, _P]),
     'rlca_ppo_loss_fwd_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float, C.c_float,
                                         _P, _P]),
+    'rlca_ppo_loss_fwd_bwd_weighted': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_float, C.c_float,
+                                                 C.c_float, C.c_float, _P, _P]),
     'rlca_policy_backward': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
     'rlca_adam_step': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                  C.c_float, _P]),

@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(1024) ppo_loss_kernel(const float *__restrict_
                                                         const float *__restrict__ mean, const float *__restrict__ action,
                                                         const float *__restrict__ old_lp, const float *__restrict__ adv,
                                                         const float *__restrict__ target, int nb, float clip,
-                                                        float coeff_entropy, float value_coef,
+                                                        float coeff_entropy, float value_coef, float weight,
                                                         float *__restrict__ dOut, float *__restrict__ losses,
                                                         float *__restrict__ dlogstd)
 {
@@ -843,6 +843,7 @@ __global__ void __launch_bounds__(1024) ppo_loss_kernel(const float *__restrict_
     const float ls0 = logstd[0], ls1 = logstd[1];
     const float var0 = expf(2.0f * ls0), var1 = expf(2.0f * ls1);
     const float inv_nb = 1.0f / (float)nb;
+    const float ginv = weight * inv_nb;          // gradients carry the data-parallel row weight, the logged losses do not
     float s_pl = 0.f, s_vl = 0.f, s_g0 = 0.f, s_g1 = 0.f;
     for (int i = threadIdx.x; i < nb; i += 1024) {
         const float m0 = mean[2 * i], m1 = mean[2 * i + 1];
@@ -857,12 +858,12 @@ __global__ void __launch_bounds__(1024) ppo_loss_kernel(const float *__restrict_
         s_vl += dv * dv;
         // d(-mean(min))/d lp : gradient flows through s1 when s1 <= s2 (ties split evenly in torch and both
         // halves reach `ratio`), else through the clamp, which is flat outside its range.
-        const float g_lp = (s1 <= s2) ? -inv_nb * A * ratio : 0.0f;
+        const float g_lp = (s1 <= s2) ? -ginv * A * ratio : 0.0f;
         const float dm0 = g_lp * d0 / var0, dm1 = g_lp * d1 / var1;      // dL/dmean
         s_g0 += g_lp * (d0 * d0 / var0 - 1.0f);
         s_g1 += g_lp * (d1 * d1 / var1 - 1.0f);
         reinterpret_cast<float4 *>(dOut)[i] =
-            make_float4(value_coef * 2.0f * dv * inv_nb, dm0 * m0 * (1.0f - m0), dm1 * (1.0f - m1 * m1), 0.0f);
+            make_float4(value_coef * 2.0f * dv * ginv, dm0 * m0 * (1.0f - m0), dm1 * (1.0f - m1 * m1), 0.0f);
     }
     const float pl = block_sum_1024(s_pl, sh), vl = block_sum_1024(s_vl, sh);
     const float g0 = block_sum_1024(s_g0, sh), g1 = block_sum_1024(s_g1, sh);
@@ -870,8 +871,8 @@ __global__ void __launch_bounds__(1024) ppo_loss_kernel(const float *__restrict_
         losses[0] = -pl * inv_nb;                              // policy_loss
         losses[1] = vl * inv_nb;                               // value_loss
         losses[2] = (0.5f + LOG_2PI_HALF + ls0) + (0.5f + LOG_2PI_HALF + ls1);   // dist_entropy (model/net.py:78-79)
-        dlogstd[0] = g0 - coeff_entropy;
-        dlogstd[1] = g1 - coeff_entropy;
+        dlogstd[0] = g0 - coeff_entropy * weight;
+        dlogstd[1] = g1 - coeff_entropy * weight;
     }
 }
 
@@ -1225,12 +1226,21 @@ extern "C" int rlca_ppo_loss_fwd_bwd(rlca_policy *pol, const float *params, cons
                                      const float *target, int32_t nb, float clip_value, float coeff_entropy,
                                      float value_coef, float *losses, void *stream)
 {
+    return rlca_ppo_loss_fwd_bwd_weighted(pol, params, value, mean, action, old_logprob, adv, target, nb, clip_value,
+                                          coeff_entropy, value_coef, 1.0f, losses, stream);
+}
+
+extern "C" int rlca_ppo_loss_fwd_bwd_weighted(rlca_policy *pol, const float *params, const float *value, const float *mean,
+                                              const float *action, const float *old_logprob, const float *adv,
+                                              const float *target, int32_t nb, float clip_value, float coeff_entropy,
+                                              float value_coef, float grad_weight, float *losses, void *stream)
+{
     if (!pol || !params || !value || !mean || !action || !old_logprob || !adv || !target || !losses)
         return rlca_set_err(RLCA_ERR_INVALID, "NULL argument");
     if (nb < 1 || nb > pol->max_batch) return rlca_set_err(RLCA_ERR_INVALID, "nb exceeds the workspace max_batch");
     ppo_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params + tensor_offset(T_LOGSTD), value, mean, action,
                                                          old_logprob, adv, target, nb, clip_value, coeff_entropy,
-                                                         value_coef, pol->dOut, losses, pol->red);
+                                                         value_coef, grad_weight, pol->dOut, losses, pol->red);
     pol->launches += 1;
     RLCA_CUDA_TRY(cudaGetLastError());
     return RLCA_OK;

@@ -115,7 +115,11 @@ def _gather(lib, src, idx, row, dst, dev):
 
 def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_entropy, clip_value, num_step, num_env,
                 frames, obs_size, act_size, filter_index=None, drop_last=False, generator=None, process_group=None,
-                value_coef=20.0):
+                value_coef=20.0, permutations=None):
+    """Body shared by ppo_update_stage1/2.  `permutations` (optional, one index array per epoch into the KEPT rows)
+    replays a recorded SubsetRandomSampler order instead of drawing one (parity tests against the reference).
+    Under a process group the minibatch schedule is agreed across ranks first (parallel.plan_minibatches), so ranks
+    with different row counts issue the same number of all-reduces."""
     lib = _lib.load()
     obss, goals, speeds, actions, logprobs, targets, values, rewards, advs = memory
     dev = policy.device
@@ -134,10 +138,13 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
         keep = keep[mask]
     n = keep.numel()
     world = 1
+    group = None if process_group in (None, True) else process_group
     if process_group is not None:
         import torch.distributed as dist
-        world = dist.get_world_size()
+        world = dist.get_world_size(group)
+    from ..parallel import average_gradients, plan_minibatches
     bs = batch_size
+    nbatches, sizes, weights = plan_minibatches(n, bs, drop_last, group, distributed=process_group is not None)
     b_obs = torch.empty(bs, frames * obs_size, device=dev)
     b_gs = torch.empty(bs, 4, device=dev)
     b_act = torch.empty(bs, act_size, device=dev)
@@ -146,30 +153,35 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
     b_tgt = torch.empty(bs, device=dev)
     v = torch.empty(bs, device=dev)
     mean = torch.empty(bs, 2, device=dev)
-    nbatches = (n // bs) if drop_last else ((n + bs - 1) // bs)
     log = torch.zeros(max(1, epoch * nbatches), 3, device=dev)
     ws = policy._workspace(bs)
     st = _stream(dev)
     k = 0
     for update in range(epoch):
-        perm = keep[torch.randperm(n, device=dev, generator=generator)]     # SubsetRandomSampler (model/ppo.py:159)
+        if permutations is not None:
+            perm = keep[torch.as_tensor(permutations[update], device=dev, dtype=torch.long)]
+        else:
+            perm = keep[torch.randperm(n, device=dev, generator=generator)]     # SubsetRandomSampler (model/ppo.py:159)
         for bi in range(nbatches):
-            index = perm[bi * bs:(bi + 1) * bs].contiguous()
-            nb = index.numel()
-            _gather(lib, obss, index, frames * obs_size, b_obs, dev)
-            _gather(lib, gs, index, 4, b_gs, dev)
-            _gather(lib, actions, index, act_size, b_act, dev)
-            _gather(lib, logprobs, index, 1, b_lp, dev)
-            _gather(lib, advs, index, 1, b_adv, dev)
-            _gather(lib, targets, index, 1, b_tgt, dev)
-            _lib.check(lib.rlca_policy_forward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(v), _ptr(mean), st))
-            _lib.check(lib.rlca_ppo_loss_fwd_bwd(ws, _ptr(policy.flat), _ptr(v), _ptr(mean), _ptr(b_act), _ptr(b_lp),
-                                                 _ptr(b_adv), _ptr(b_tgt), nb, clip_value, coeff_entropy, value_coef,
-                                                 _ptr(log[k]), st))
-            _lib.check(lib.rlca_policy_backward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(policy.grad), st))
+            nb = sizes[bi]
+            if nb > 0:
+                index = perm[bi * bs:bi * bs + nb].contiguous()
+                _gather(lib, obss, index, frames * obs_size, b_obs, dev)
+                _gather(lib, gs, index, 4, b_gs, dev)
+                _gather(lib, actions, index, act_size, b_act, dev)
+                _gather(lib, logprobs, index, 1, b_lp, dev)
+                _gather(lib, advs, index, 1, b_adv, dev)
+                _gather(lib, targets, index, 1, b_tgt, dev)
+                _lib.check(lib.rlca_policy_forward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(v), _ptr(mean), st))
+                _lib.check(lib.rlca_ppo_loss_fwd_bwd_weighted(ws, _ptr(policy.flat), _ptr(v), _ptr(mean), _ptr(b_act),
+                                                              _ptr(b_lp), _ptr(b_adv), _ptr(b_tgt), nb, clip_value,
+                                                              coeff_entropy, value_coef, float(weights[bi]),
+                                                              _ptr(log[k]), st))
+                _lib.check(lib.rlca_policy_backward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(policy.grad), st))
+            else:
+                policy.grad.zero_()             # this rank ran out of rows: it still takes part in the all-reduce
             if process_group is not None:
-                from ..parallel import average_gradients
-                average_gradients(policy.grad, None if process_group is True else process_group)
+                average_gradients(policy.grad, group)
             optimizer.step(grad_scale=1.0 / world)
             k += 1
     rows = log[:k].cpu().tolist()
@@ -179,18 +191,21 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
 
 
 def ppo_update_stage1(policy, optimizer, batch_size, memory, epoch, coeff_entropy=0.02, clip_value=0.2, num_step=2048,
-                      num_env=12, frames=1, obs_size=24, act_size=4, generator=None, process_group=None):
+                      num_env=12, frames=1, obs_size=24, act_size=4, generator=None, process_group=None,
+                      permutations=None):
     """model/ppo.py:143-194 (drop_last=False)."""
     rows = _ppo_update(policy, optimizer, batch_size, memory, epoch, coeff_entropy, clip_value, num_step, num_env,
-                       frames, obs_size, act_size, None, False, generator, process_group)
+                       frames, obs_size, act_size, None, False, generator, process_group, permutations=permutations)
     print('update')
     return rows
 
 
 def ppo_update_stage2(policy, optimizer, batch_size, memory, filter_index, epoch, coeff_entropy=0.02, clip_value=0.2,
-                      num_step=2048, num_env=12, frames=1, obs_size=24, act_size=4, generator=None, process_group=None):
+                      num_step=2048, num_env=12, frames=1, obs_size=24, act_size=4, generator=None, process_group=None,
+                      permutations=None):
     """model/ppo.py:197-259 (filtered transitions deleted, drop_last=True)."""
     rows = _ppo_update(policy, optimizer, batch_size, memory, epoch, coeff_entropy, clip_value, num_step, num_env,
-                       frames, obs_size, act_size, filter_index, True, generator, process_group)
+                       frames, obs_size, act_size, filter_index, True, generator, process_group,
+                       permutations=permutations)
     print('filter {} transitions; update'.format(len(filter_index)))
     return rows

@@ -44,3 +44,53 @@ def broadcast_parameters(flat: torch.Tensor, src=0, group=None):
     import torch.distributed as dist
     dist.broadcast(flat, src=src, group=group)
     return flat
+
+
+def plan_minibatches(n_local: int, batch_size: int, drop_last: bool, group=None, distributed: bool = False):
+    """Agree on ONE minibatch schedule per epoch across ranks whose row counts differ (stage 2 deletes the rows of
+    `filter_index` per rank, model/ppo.py:212-218; uneven world shards give different T*N per rank).
+
+    Every rank must issue the same number of gradient all-reduces, so the step count is global:
+      drop_last (stage 2, model/ppo.py:221-223): steps = min over ranks of n_r // batch_size; every minibatch is full,
+          a rank with more rows drops a longer (random, re-drawn every epoch) tail - the reference's own rule applied
+          to the rank that binds;
+      otherwise (stage 1, :159-160): steps = max over ranks of ceil(n_r / batch_size); a rank that runs out of rows
+          takes a short or EMPTY minibatch (zero gradient, still all-reduces).
+    Returns (steps, sizes, weights): sizes[i] = rows this rank uses in step i, weights[i] = sizes[i] * world /
+    sum over ranks of sizes[i], the factor that makes (all-reduced gradient / world) the mean over all rows of the
+    global minibatch (rlca_ppo_loss_fwd_bwd_weighted)."""
+    counts = [int(n_local)]
+    rank = 0
+    if distributed:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        rank = dist.get_rank(group)
+        t = torch.zeros(world, dtype=torch.int64)
+        t[rank] = int(n_local)
+        backend = dist.get_backend(group)
+        if backend == 'nccl':
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        counts = [int(x) for x in t.cpu().tolist()]
+    world = len(counts)
+    bs = int(batch_size)
+    if drop_last:
+        steps = min(c // bs for c in counts)
+    else:
+        steps = max((c + bs - 1) // bs for c in counts)
+    sizes, weights = [], []
+    for i in range(steps):
+        per_rank = [min(bs, max(0, c - i * bs)) for c in counts]
+        tot = sum(per_rank)
+        sizes.append(per_rank[rank])
+        weights.append(per_rank[rank] * world / tot if tot else 0.0)
+    return steps, sizes, weights
+
+
+def agree_to_stop(local_stop: bool, device=None, group=None) -> bool:
+    """True on every rank as soon as ANY rank wants to leave the training loop (the exit test uses rank-local episode
+    counts; a rank that left alone would strand the others in the next all-reduce)."""
+    import torch.distributed as dist
+    t = torch.tensor([1.0 if local_stop else 0.0], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return bool(t.item() > 0)

@@ -26,6 +26,7 @@ sm_100a CUDA behind the C ABI of include/rlca.h); torch only owns the memory.
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import numpy as np
 import torch
@@ -82,6 +83,7 @@ class StageWorld:
         self._action = torch.zeros(N, 2, device=dev)
         self._host = None
         self._host_ptrs = None
+        self._ticked = False
         self.reset_world()
 
     # ------------------------------------------------------------------ plumbing
@@ -140,6 +142,7 @@ class StageWorld:
         st = self._state_struct(self._cur)
         none = torch.zeros(self.N, dtype=torch.uint8, device=self.device)
         _lib.check(self.lib.rlca_env_reset(self._h, C.byref(st), _ptr(none), 1, self._stream()))
+        self._ticked = False
 
     def reset_pose(self, mask=None):
         """reset_pose + generate_goal_point for the masked agents (all when None).  The goal is
@@ -150,9 +153,44 @@ class StageWorld:
         self._observe()
 
     def generate_goal_point(self, mask=None):
-        """Goal already drawn by reset_pose (same kernel); kept for call-order compatibility
-        (ppo_stage1.py:51-53)."""
-        return None
+        """generate_goal_point (stage_world1.py:171-177): a goal for the CURRENT pose of the masked agents (all when
+        None), pre_distance refreshed.  The draws are keyed by (agent, episode), so right after reset_pose this
+        re-derives the goal reset_pose already drew - the reference's call order (ppo_stage1.py:51-53) is harmless."""
+        st = self._state_struct(self._cur)
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.lib.rlca_env_reset(self._h, C.byref(st), _ptr(m), 2, self._stream()))
+        self._observe()
+
+    def generate_random_goal(self):
+        """(N, 2) goals generate_goal_point would set for the current poses (stage_world1.py:262-274 and the stage-2 /
+        circle variants), without touching the state."""
+        return self._scratch_reset(2)['goal'][:, 0:2]
+
+    def generate_random_pose(self):
+        """(N, 3) poses the next reset_pose would teleport to (stage_world1.py:251-260; table poses where the scenario
+        does not randomise), without touching the state."""
+        return self._scratch_reset(0)['pose'][:, 0:3]
+
+    def _scratch_reset(self, mode):
+        sc = {k: v.clone() for k, v in self.state.items()}
+        st = _lib.EnvState(_ptr(sc['pose']), _ptr(sc['goal']), _ptr(sc['acc']), _ptr(sc['meta']))
+        _lib.check(self.lib.rlca_env_reset(self._h, C.byref(st), _ptr(None), mode, self._stream()))
+        return sc
+
+    def control_pose(self, pose, mask=None):
+        """cmd_pose (stage_world1.py:237-249 -> stageros.cpp:282-296): teleport the masked agents (all when None) to
+        pose (N, 3) = x, y, yaw; no collision test, stall flag untouched; the next scan is taken from the new pose."""
+        p = pose.to(device=self.device, dtype=torch.float32).reshape(self.N, 3)
+        th = torch.remainder(p[:, 2] + math.pi, 2 * math.pi) - math.pi          # yaw read back in (-pi, pi]
+        th = torch.where(th <= -math.pi, th + 2 * math.pi, th)
+        new = torch.stack((p[:, 0], p[:, 1], th), 1)
+        cur = self.state['pose']
+        if mask is None:
+            cur[:, 0:3] = new
+        else:
+            m = mask.to(device=self.device).bool()
+            cur[m, 0:3] = new[m]
+        self._observe()
 
     def _observe(self, obs=None):
         st = self._state_struct(self._cur)
@@ -172,6 +210,7 @@ class StageWorld:
         self._last_out = out or {}
         _lib.check(self.lib.rlca_env_step(self._h, C.byref(s_in), C.byref(s_out), C.byref(io), self._stream()))
         self._cur = 1 - self._cur
+        self._ticked = True
 
     def get_reward_and_terminate(self, t=None):
         """(reward, terminate, result) of the tick just run (stage_world1.py:180-211).  The step
@@ -194,6 +233,18 @@ class StageWorld:
 
     def get_self_state(self):
         return self.state['pose'][:, 0:3]
+
+    def get_self_speedGT(self):
+        """(N, 2) ground-truth speed as stageros publishes it (stage_world1.py:88-95,119-120; stageros.cpp:580-606):
+        |pose - previous pose| / dt and normalize(yaw - previous yaw) / dt, teleports included.  Zero before the
+        first tick.  (The tick keeps both poses: the state is ping-ponged.)"""
+        if not self._ticked:
+            return torch.zeros(self.N, 2, device=self.device)
+        cur, prev = self._st[self._cur]['pose'], self._st[1 - self._cur]['pose']
+        d = cur[:, 0:3] - prev[:, 0:3]
+        a = torch.remainder(d[:, 2] + math.pi, 2 * math.pi) - math.pi
+        inv_dt = 1.0 / float(self.cfg.dt)
+        return torch.stack((torch.hypot(d[:, 0], d[:, 1]) * inv_dt, a * inv_dt), 1)
 
     def get_crash_state(self):
         return self.state['meta'][:, 2].to(torch.uint8)
@@ -240,6 +291,7 @@ class StageWorld:
             self._h, C.byref(s_in), C.byref(s_out), C.byref(io), _ptr(action_host),
             p_obs if want_obs else p_null, p_rew, p_flg, p_gs, self._stream()))
         self._cur = 1 - self._cur
+        self._ticked = True
         return h
 
     def raycast(self, pose, normalise=False, out=None):

@@ -34,9 +34,10 @@ class Rollout:
 
 
 def run(env, policy, policy_path, action_bound, optimizer, hp, logger=None, logger_cal=None, stage=1, max_updates=None,
-        process_group=None, rank=0, save_every=20, generator=None):
+        process_group=None, rank=0, save_every=20, generator=None, start_update=0):
     """hp: dict with HORIZON, GAMMA, LAMDA, BATCH_SIZE, EPOCH, COEFF_ENTROPY, CLIP_VALUE, NUM_ENV, OBS_SIZE, ACT_SIZE,
-    LASER_HIST, MAX_EPISODES.  Returns per-update stats (for tests / benchmarks)."""
+    LASER_HIST, MAX_EPISODES.  `start_update` continues the checkpoint numbering of a resumed run.
+    Returns per-update stats (for tests / benchmarks)."""
     H, N = hp['HORIZON'], env.N
     dev = env.device
     ro = Rollout(H, N, env.beam_mum, dev)
@@ -46,7 +47,8 @@ def run(env, policy, policy_path, action_bound, optimizer, hp, logger=None, logg
     obs = env.get_laser_observation()
     ro.stacks[0] = obs[:, None, :]                      # deque([obs, obs, obs]) (:60)
     ro.gs[0] = env.gs
-    global_update = 0
+    global_update = int(start_update)
+    updates_done = 0
     episodes = 0
     stats = []
     while True:
@@ -78,6 +80,7 @@ def run(env, policy, policy_path, action_bound, optimizer, hp, logger=None, logg
         torch.cuda.synchronize(dev)
         t2 = time.perf_counter()
         global_update += 1
+        updates_done += 1
         # ---- episode log lines (ppo_stage1.py:127-131 / ppo_stage2.py:136-137), one D2H per update
         fl = ro.flags.cpu().numpy()
         ended = (fl[:, :, 0] != 0) & (fl[:, :, 2] != 0) if stage == 2 else (fl[:, :, 0] != 0)
@@ -112,8 +115,11 @@ def run(env, policy, policy_path, action_bound, optimizer, hp, logger=None, logg
         # carry the state over the horizon boundary
         ro.stacks[0].copy_(ro.stacks[H])
         ro.gs[0].copy_(ro.gs[H])
-        if max_updates is not None and global_update >= max_updates:
-            break
-        if episodes >= hp['MAX_EPISODES'] * N:
+        stop = (max_updates is not None and updates_done >= max_updates) or episodes >= hp['MAX_EPISODES'] * N
+        if process_group is not None:
+            # episode counts are rank-local: leave together, or the others hang in the next all-reduce
+            from .parallel import agree_to_stop
+            stop = agree_to_stop(stop, dev, None if process_group is True else process_group)
+        if stop:
             break
     return stats

@@ -56,3 +56,11 @@ def synthetic_rollout(T, N, seed=5, with_obs=False):
         out['action'] = action.reshape(T, N, 2)
         out['logprob'] = rs.uniform(-1.5, 0.5, size=(T, N, 1)).astype(np.float32)
     return out
+
+
+def stage2_rollout(T=6, N=8):
+    """Rollout for the ppo_update_stage2 golden: done flags dense enough (45 %) that get_filter_index finds runs of
+    consecutive terminal steps (the rows stage 2 deletes, model/utils.py:65-78)."""
+    roll = synthetic_rollout(T=T, N=N, seed=11, with_obs=True)
+    roll['dones'] = np.random.RandomState(21).rand(T, N) < 0.45
+    return roll

@@ -304,3 +304,81 @@ def test_circle_world_global_grid_path(built):
     got = env.raycast(torch.from_numpy(pose).cuda()).cpu().numpy()
     ref = orc.raycast(pose)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize('scenario', ['stage1', 'stage2'])
+def test_env_surface_leftovers(built, scenario):
+    """generate_goal_point alone / generate_random_goal / generate_random_pose / control_pose / get_self_speedGT
+    (stage_world1.py:119-120,171-177,237-274 and the stage-2 variants)."""
+    sc, env, orc = make_pair(scenario, num_worlds=3, seed=17)
+    env.reset_pose()
+    orc.reset_world()
+    orc.reset_pose()
+    before = {k: v.clone() for k, v in env.state.items()}
+    # the reference's call order reset_pose -> generate_goal_point re-derives the same goal: nothing changes
+    env.generate_goal_point()
+    orc.generate_goal_point()
+    assert_state_equal(env, orc, 'generate_goal_point after reset_pose')
+    for k, v in before.items():
+        assert torch.equal(v, env.state[k]), k
+    # the pose the NEXT reset_pose will use, without touching the state
+    nxt = env.generate_random_pose().cpu().numpy()
+    for k, v in before.items():
+        assert torch.equal(v, env.state[k]), k
+    # teleport two thirds of the robots, then a goal for where they are now
+    rng = np.random.default_rng(3)
+    new = np.stack([rng.uniform(-6, 6, orc.N), rng.uniform(-6, 6, orc.N), rng.uniform(-7, 7, orc.N)], 1).astype(np.float32)
+    if scenario == 'stage2':
+        new[:, 0] += 12.0
+        new[:, 1] -= 8.0
+    mask = (np.arange(orc.N) % 3 != 0)
+    env.control_pose(torch.from_numpy(new), mask=torch.from_numpy(mask))
+    th = np.float32(new[:, 2])
+    got = env.state['pose'].cpu().numpy()
+    assert np.array_equal(got[~mask], before['pose'].cpu().numpy()[~mask])
+    assert np.allclose(got[mask, :2], new[mask, :2]) and np.all(np.abs(got[:, 2]) <= np.pi + 1e-6)
+    assert np.allclose(np.cos(got[mask, 2]), np.cos(th[mask]), atol=1e-5) and np.allclose(np.sin(got[mask, 2]), np.sin(th[mask]), atol=1e-5)
+    assert np.array_equal(env.state['meta'].cpu().numpy(), before['meta'].cpu().numpy())     # stall / counters untouched
+    orc.pose[:] = got                                         # same poses on the oracle side, then compare the scans
+    orc.observe()
+    assert_outputs_equal(env, orc, 'scan after control_pose')
+    want_goal = env.generate_random_goal().cpu().numpy()
+    env.generate_goal_point(mask=torch.from_numpy(mask))
+    orc.generate_goal_point(mask.astype(np.uint8))
+    assert_state_equal(env, orc, 'generate_goal_point for the teleported robots')
+    assert_outputs_equal(env, orc, 'local goal after generate_goal_point')
+    assert np.array_equal(env.state['goal'].cpu().numpy()[mask, :2], want_goal[mask])
+    if scenario == 'stage1':
+        d = np.hypot(*(env.state['goal'].cpu().numpy()[mask, :2] - got[mask, :2]).T)
+        assert np.all((d >= 8.0 - 1e-4) & (d <= 10.0 + 1e-4))          # generate_random_goal's acceptance ring
+    # ground-truth speed: zero before a tick, then |dpose| / dt
+    assert float(env.get_self_speedGT().abs().max()) == 0.0
+    prev = env.state['pose'].cpu().numpy().copy()
+    a = random_actions(rng, orc.N)
+    env.control_vel(torch.from_numpy(a).cuda())
+    cur = env.state['pose'].cpu().numpy()
+    gt = env.get_self_speedGT().cpu().numpy()
+    dth = (cur[:, 2] - prev[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    assert np.allclose(gt[:, 0], np.hypot(cur[:, 0] - prev[:, 0], cur[:, 1] - prev[:, 1]) * 10, atol=1e-4)
+    assert np.allclose(gt[:, 1], dth * 10, atol=1e-4)
+    moved = (env.flags.cpu().numpy()[:, 1] == 0) & (env.flags.cpu().numpy()[:, 3] == 0)
+    assert np.allclose(gt[moved, 0], np.clip(a[moved, 0], 0, 1), atol=2e-4)      # un-crashed robots move at the command
+    # and the pose generate_random_pose announced is the one reset_pose uses
+    env.control_pose(torch.from_numpy(before['pose'].cpu().numpy()[:, :3]))
+    env._st[env._cur]['meta'].copy_(before['meta'])
+    env.reset_pose()
+    assert np.array_equal(env.state['pose'].cpu().numpy()[:, :3], nxt)
+
+
+def test_config_limits_are_rejected(built):
+    """range_cells >= 2048 would overflow the 12-bit fields of the lidar walk key: loud error, not wrong ranges."""
+    import ctypes as C
+    from rl_collision_avoidance_b200 import _lib
+    from rl_collision_avoidance_b200.scenarios import fill_config, make_scenario
+    lib = _lib.load()
+    sc = make_scenario('stage1')
+    cfg = fill_config(_lib.EnvConfig(), sc, num_worlds=1, beams=512)
+    cfg.range_cells = 2500.0
+    h = C.c_void_p()
+    assert lib.rlca_env_create(C.byref(cfg), C.byref(h)) != 0
+    assert b'range_cells' in lib.rlca_last_error()

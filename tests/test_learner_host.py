@@ -52,3 +52,28 @@ def test_golden_file_is_from_the_reference():
     assert np.allclose(g['gae_small_targets'], [[1.0198, 3.592677], [0.0, 3.788385], [1.099, 1.891]], atol=1e-6)
     assert np.allclose(g['gae_small_advs'], [[0.5198, 3.092677], [-0.4, 3.188385], [0.799, 1.691]], atol=1e-6)
     assert g['ppo_losses'].shape == (3, 3)
+
+
+def test_stage2_golden_filter_is_our_filter():
+    """The rows the reference's ppo_update_stage2 golden deleted are get_filter_index of the same done flags."""
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from golden_inputs import stage2_rollout
+    from rl_collision_avoidance_b200.model.utils import get_filter_index
+    g = np.load(GOLD)
+    assert [int(i) for i in get_filter_index(stage2_rollout()['dones'])] == g['ppo2_filter_index'].tolist()
+    n_kept = 48 - len(g['ppo2_filter_index'])
+    assert g['ppo2_perms'].shape == (2, n_kept) and n_kept % int(g['ppo2_batch_size']) != 0
+
+
+def test_reference_checkpoint_fixtures_have_the_23_tensors():
+    """tests/golden/checkpoints/*.pth are the reference's shipped policy/*.pth (data fixtures): same keys and shapes as
+    our flat parameter layout."""
+    sys_path = os.path.dirname(__file__)
+    import sys
+    sys.path.insert(0, sys_path)
+    from golden_inputs import SHAPES
+    for name in ('stage1_1', 'stage1_2', 'stage2'):
+        sd = torch.load(os.path.join(sys_path, 'golden', 'checkpoints', name + '.pth'), map_location='cpu')
+        assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s)) for k, s in SHAPES]
+        assert all(v.dtype == torch.float32 for v in sd.values())

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from rl_collision_avoidance_b200.parallel import (allreduce_moments, average_gradients, broadcast_parameters,
-                                                 normalize_from_moments, shard_worlds)
+                                                 normalize_from_moments, plan_minibatches, shard_worlds, agree_to_stop)
 
 
 def test_shard_worlds_covers_everything_once():
@@ -69,3 +69,62 @@ def test_world_size_2_gloo_collectives():
         assert p.exitcode == 0
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+def test_plan_minibatches_single_process():
+    steps, sizes, weights = plan_minibatches(41, 16, drop_last=True)
+    assert (steps, sizes, weights) == (2, [16, 16], [1.0, 1.0])
+    steps, sizes, weights = plan_minibatches(41, 16, drop_last=False)
+    assert (steps, sizes, weights) == (3, [16, 16, 9], [1.0, 1.0, 1.0])
+    assert plan_minibatches(5, 16, drop_last=True)[0] == 0
+
+
+def _sched_worker(rank, world_size, port, out):
+    """Ranks with DIFFERENT row counts (stage 2: per-rank filter_index; model/ppo.py:212-223) must issue the same
+    number of gradient all-reduces, and the weighted average must equal the gradient of the global minibatch."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    try:
+        n_local = [70, 41][rank]
+        rs = np.random.RandomState(3)
+        rows_all = [torch.from_numpy(rs.standard_normal((70, 5))), torch.from_numpy(rs.standard_normal((41, 5)))]
+        rows = rows_all[rank]
+        res = {}
+        for drop_last in (True, False):
+            steps, sizes, weights = plan_minibatches(n_local, 16, drop_last, distributed=True)
+            reduces = 0
+            ok = True
+            for i in range(steps):
+                nb = sizes[i]
+                # "gradient" of a mean loss over this rank's rows of the step, times the data-parallel weight
+                g = rows[i * 16:i * 16 + nb].mean(0) * weights[i] if nb else torch.zeros(5, dtype=torch.float64)
+                average_gradients(g)
+                reduces += 1
+                g = g / world_size
+                union = torch.cat([r[i * 16:i * 16 + min(16, max(0, len(r) - i * 16))] for r in rows_all])
+                ok = ok and bool((g - union.mean(0)).abs().max() < 1e-12)
+            res[drop_last] = (steps, reduces, ok, sizes)
+        stop = agree_to_stop(rank == 1)            # only rank 1 wants to stop: both must
+        out.put((rank, res, stop))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_different_row_counts_same_collective_count():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sched_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, a, stop0), (r1, b, stop1) = res
+    assert stop0 and stop1
+    assert a[True][:3] == (2, 2, True) and b[True][:3] == (2, 2, True)           # min(70 // 16, 41 // 16) full batches
+    assert a[True][3] == [16, 16] and b[True][3] == [16, 16]
+    assert a[False][:3] == (5, 5, True) and b[False][:3] == (5, 5, True)         # max(ceil(70/16), ceil(41/16))
+    assert a[False][3] == [16, 16, 16, 16, 6] and b[False][3] == [16, 16, 9, 0, 0]

@@ -16,7 +16,7 @@ REF = os.environ.get('RLCA_REFERENCE', '/root/reference')
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
-from golden_inputs import synthetic_state_dict, synthetic_batch, synthetic_rollout  # noqa: E402
+from golden_inputs import stage2_rollout, synthetic_state_dict, synthetic_batch, synthetic_rollout  # noqa: E402
 
 
 def main():
@@ -118,6 +118,69 @@ def main():
     out['grad_act_fc1.weight_rows'] = g['act_fc1.weight'][::37, ::301]
     out['grad_crt_fc1.weight_rows'] = g['crt_fc1.weight'][::41, ::307]
     out['loss0'] = np.array([pl.item(), vl.item(), ent.item()])
+
+    # ---- ppo_update_stage2 (model/ppo.py:197-259): rows in filter_index deleted after the normalisation over ALL rows
+    # (:200 before :212-218), BatchSampler(drop_last=True) (:221-223) so the ragged tail of every epoch is skipped.
+    # The minibatch membership depends on torch.randperm inside SubsetRandomSampler; the permutations the reference drew
+    # are recorded so that our side replays exactly the same minibatches.
+    T2, N2 = 6, 8
+    roll2 = stage2_rollout(T2, N2)
+    pol = CNNPolicy(frames=3, action_space=2)
+    pol.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    opt = torch.optim.Adam(pol.parameters(), lr=5e-5)
+    tg2, adv2 = ref_ppo.generate_train_data(roll2['rewards'].astype(np.float64), 0.99, roll2['values'].astype(np.float64),
+                                            roll2['last_value'].astype(np.float64), roll2['dones'].astype(np.float64), 0.95)
+    filt = ref_utils.get_filter_index(roll2['dones'])
+    assert len(filt) >= 3, filt                               # the filter must be non-trivial
+    memory2 = (roll2['obs'].astype(np.float64), roll2['goal'].astype(np.float64), roll2['speed'].astype(np.float64),
+               roll2['action'], roll2['logprob'], tg2, roll2['values'], roll2['rewards'], adv2)
+    perms = []
+    real_randperm = torch.randperm
+
+    def rec_randperm(n, *a, **k):
+        p = real_randperm(n, *a, **k)
+        perms.append(p.numpy().copy())
+        return p
+    torch.randperm = rec_randperm
+    torch.manual_seed(2024)
+    rows = []
+    bs2 = 16
+    try:
+        ref_ppo.ppo_update_stage2(policy=pol, optimizer=opt, batch_size=bs2, memory=memory2, filter_index=filt, epoch=2,
+                                  coeff_entropy=5e-4, clip_value=0.1, num_step=T2, num_env=N2, frames=3, obs_size=512,
+                                  act_size=2)
+    finally:
+        torch.randperm = real_randperm
+    n_kept = T2 * N2 - len(filt)
+    assert len(perms) == 2 and all(len(p) == n_kept for p in perms), (len(perms), n_kept)
+    assert n_kept % bs2 != 0 and len(rows) == 2 * (n_kept // bs2), (n_kept, len(rows))     # ragged tail dropped
+    out['ppo2_filter_index'] = np.asarray(filt, np.int64)
+    out['ppo2_perms'] = np.stack(perms).astype(np.int64)
+    out['ppo2_batch_size'] = np.int64(bs2)
+    out['ppo2_losses'] = np.asarray(rows, np.float64)
+    after = pol.state_dict()
+    out['ppo2_logstd_after'] = after['logstd'].numpy()
+    for k in ('act_fea_cv1.weight', 'act_fea_cv2.bias', 'act_fc1.bias', 'act_fc2.weight', 'actor1.weight', 'actor2.bias',
+              'crt_fea_cv1.bias', 'crt_fea_cv2.weight', 'crt_fc2.bias', 'critic.weight', 'critic.bias'):
+        out['ppo2_after_' + k] = after[k].numpy()
+    out['ppo2_after_act_fc1.weight_rows'] = after['act_fc1.weight'].numpy()[::37, ::301]
+    out['ppo2_after_crt_fc1.weight_rows'] = after['crt_fc1.weight'].numpy()[::41, ::307]
+
+    # ---- the reference's shipped checkpoints (policy/*.pth, loaded at ppo_stage1.py:185-191 / ppo_stage2.py:194-200 /
+    # circle_test.py:97-103): SURVEY App. C's free / ramp probes through the reference's own CNNPolicy
+    free_obs = torch.full((1, 3, 512), 0.5)
+    ramp_obs = (torch.arange(512, dtype=torch.float32) / 511 - 0.5).view(1, 1, 512).repeat(1, 3, 1)
+    for name in ('stage1_1', 'stage1_2', 'stage2'):
+        pol = CNNPolicy(frames=3, action_space=2)
+        pol.load_state_dict(torch.load(os.path.join(REF, 'policy', name + '.pth'), map_location='cpu'))
+        with torch.no_grad():
+            v_f, _, _, m_f = pol(free_obs, torch.tensor([[5.0, 0.0]]), torch.tensor([[0.0, 0.0]]))
+            v_r, _, _, m_r = pol(ramp_obs, torch.tensor([[3.0, -1.0]]), torch.tensor([[0.5, 0.2]]))
+            _, lp, ent = pol.evaluate_actions(free_obs, torch.tensor([[5.0, 0.0]]), torch.tensor([[0.0, 0.0]]),
+                                              torch.tensor([[0.7, 0.1]]))
+        out['ckpt_' + name] = np.array([v_f.item(), m_f[0, 0].item(), m_f[0, 1].item(), v_r.item(), m_r[0, 0].item(),
+                                        m_r[0, 1].item(), lp.item(), ent.item()], np.float64)
+        print(name, out['ckpt_' + name])
 
     path = os.path.join(ROOT, 'tests', 'golden', 'learner_golden.npz')
     np.savez_compressed(path, **out)
