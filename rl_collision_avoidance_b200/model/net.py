@@ -122,6 +122,11 @@ class CNNPolicy:
         self.grad.zero_()
 
     # ------------------------------------------------------------------ workspace
+    @property
+    def launch_count(self):
+        """Kernel launches issued through this policy's workspace (rlca_policy_launch_count)."""
+        return int(self.lib.rlca_policy_launch_count(self._ws)) if self._ws is not None else 0
+
     def _workspace(self, nb):
         if self._ws is None or nb > self._ws_batch:
             if self._ws is not None:
