@@ -119,6 +119,17 @@ typedef struct rlca_step_io {
     float *stack_out_dev;        /*   out = [in[1], in[2], new scan], or 3 x new scan after a re-spawn; both or neither */
 } rlca_step_io;
 
+/* Host-side walk tables of the table-driven lidar for a given range_cells = range_max / resolution (no device
+ * needed; the same code rlca_env_set_map runs, exported so that CPU tests can check it against the cell-by-cell
+ * walk of World::Raytrace).  Slots = the truncated end points (trunc(R cos a), trunc(R sin a)) any
+ * ray can have.  Call with NULL buffers for the sizes, then with
+ *   slot_keys   [2 * nslots] int16  (idx, idy) of every slot, ordered by angle
+ *   keyslot     [(2 kr + 1)^2] uint16  (idy + kr) * (2 kr + 1) + (idx + kr) -> slot, 0xffff = cannot occur
+ *   inv_off     [(2 kr + 1)^2 + 1], inv_ent [nentries]: per relative cell, slot | dominant-axis distance << 16 of
+ *               every walk that tests that cell. */
+int rlca_walk_tables_host(float range_cells, int32_t *kr, int32_t *nslots, int32_t *nentries, int16_t *slot_keys,
+                          uint16_t *keyslot, uint32_t *inv_off, uint32_t *inv_ent);
+
 typedef struct rlca_env rlca_env;
 
 /* Replaces StageNode construction + world->Load (stageros.cpp:311-355): creates the
@@ -188,7 +199,7 @@ int rlca_raycast(rlca_env *env, const float *pose_dev, float *ranges_dev, int32_
 /* World ranges per rlca_env_step_host call on the DMA path: 0 = library default (2),
  * 1 = strictly serial (copy in, one launch, copy out), up to 16. */
 int rlca_env_set_host_chunks(rlca_env *env, int32_t chunks);
-/* Host traffic mode of rlca_env_step_host: 0, 1 or 2 (see there). */
+/* Host traffic mode of rlca_env_step_host: 0, 1 or 2 (see there); -1 = back to the library default. */
 int rlca_env_set_host_zero_copy(rlca_env *env, int32_t mode);
 
 /* Launch shape knob: CTAs per world (>= 1).  0 = library default (auto). */
