@@ -34,6 +34,10 @@ LEARNING_RATE = 5e-5
 
 
 def enjoy(env, policy, action_bound, max_steps):
+    """The loop of /root/reference/circle_test.py:36-84, batched.  `terminal` is the terminate flag of the PREVIOUS tick
+    (not a latch), exactly as the reference carries it: a robot standing on its goal stays terminal and keeps v = 0,
+    a crashed robot that turns itself free moves again.  Returns (ever_terminal, first result code, tick of the first
+    termination, ticks run) for the metrics."""
     env.reset_world()                                           # circle_test.py:39-40
     env.reset_pose()
     env.generate_goal_point()
@@ -41,6 +45,7 @@ def enjoy(env, policy, action_bound, max_steps):
     obs = env.get_laser_observation()
     stacks = [obs[:, None, :].repeat(1, 3, 1).contiguous(), torch.empty(N, 3, LASER_BEAM, device=dev)]
     terminal = torch.zeros(N, dtype=torch.bool, device=dev)
+    ever = torch.zeros(N, dtype=torch.bool, device=dev)
     result = torch.zeros(N, dtype=torch.uint8, device=dev)
     steps_to_end = torch.zeros(N, dtype=torch.int32, device=dev)
     for step in range(1, max_steps + 1):
@@ -51,14 +56,15 @@ def enjoy(env, policy, action_bound, max_steps):
         real_action = scaled_action.clone()
         real_action[terminal, 0] = 0                            # circle_test.py:64-65
         env.control_vel(real_action, stack_in=stacks[k], stack_out=stacks[1 - k])
-        r, term, res = env.get_reward_and_terminate(step)
-        newly = term & ~terminal
+        r, terminal, res = env.get_reward_and_terminate(step)   # :70 - the flag of THIS tick drives the next one
+        terminal = terminal.clone()
+        newly = terminal & ~ever
         result[newly] = res[newly]
         steps_to_end[newly] = step
-        terminal |= term
-        if bool(terminal.all()):
+        ever |= terminal
+        if bool(ever.all()):
             break
-    return terminal, result, steps_to_end, step
+    return ever, result, steps_to_end, step
 
 
 def main():
