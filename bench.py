@@ -442,7 +442,15 @@ def section_learner_dp(torch, dist, dev, world_size):
                                              _ptr(tgt), nb, 0.1, 5e-4, 20.0, _ptr(losses), st))
         _lib.check(lib.rlca_policy_backward(ws, _ptr(pol.flat), _ptr(obs), _ptr(gs), nb, _ptr(pol.grad), st))
 
-    def full(_=0):
+    from rl_collision_avoidance_b200.parallel import OverlappedGradSync
+    sync = OverlappedGradSync(pol)
+
+    def full(_=0):                   # what model/ppo.py runs: fc-side ranges all-reduced under the rest of the backward
+        compute()
+        sync.reduce()
+        opt.step(grad_scale=1.0 / world_size)
+
+    def serial(_=0):                 # one all-reduce of the whole buffer after the backward
         compute()
         dist.all_reduce(pol.grad)
         opt.step(grad_scale=1.0 / world_size)
@@ -455,7 +463,8 @@ def section_learner_dp(torch, dist, dev, world_size):
         dist.all_reduce(pol.grad)
 
     res = {}
-    for k, fn in (('step_us', full), ('step_without_allreduce_us', local), ('allreduce_alone_us', ar)):
+    for k, fn in (('step_us', full), ('step_serial_allreduce_us', serial), ('step_without_allreduce_us', local),
+                  ('allreduce_alone_us', ar)):
         ms = gpu_time(torch, dev, fn, 20, warm=5)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -464,6 +473,8 @@ def section_learner_dp(torch, dist, dev, world_size):
     res['allreduce_share'] = max(0.0, res['step_us'] - res['step_without_allreduce_us']) / res['step_us']
     res['samples_per_s'] = nb * world_size / (res['step_us'] * 1e-6)
     res['batch_per_rank'] = nb
+    res['how'] = ('step_us: fc-side gradient ranges (97 % of 8.69 MB) all-reduced from a side stream once '
+                  'rlca_policy_backward signals them, under the dF GEMM and the conv tower backward; conv ranges after')
     return res
 
 

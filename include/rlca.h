@@ -231,6 +231,13 @@ typedef struct rlca_policy rlca_policy;   /* workspace (activations kept for bac
 int64_t rlca_policy_param_offset(int32_t tensor_index);
 int64_t rlca_policy_param_size(int32_t tensor_index);     /* unpadded element count of tensor i */
 int64_t rlca_policy_launch_count(const rlca_policy *pol);
+
+/* Data-parallel overlap hook (model/ppo.py:186-188 takes an optimizer step per minibatch, so the gradient all-reduce is
+ * on the critical path): `event` (a cudaEvent_t, or NULL to clear) is recorded by every rlca_policy_backward on its
+ * stream as soon as all gradients OUTSIDE the two conv towers are final - fc1/fc2/heads, 97 % of the flat buffer,
+ * tensors 5..12 and 17..22 of the state_dict order.  The caller all-reduces those ranges on another stream while the
+ * dF GEMM and the conv tower backward are still running, and the conv ranges afterwards. */
+int rlca_policy_set_grad_event(rlca_policy *pol, void *event);
 /* Conv tower + fc1 forward/backward GEMMs on the tcgen05 tensor cores with 3xTF32 error compensation
  * (enable = 1, the default); 2 = fc1 GEMMs only; 0 selects the plain fp32 CUDA-core kernels (kept as the
  * cross-check for the tensor-core path). */

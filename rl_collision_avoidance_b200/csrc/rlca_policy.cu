@@ -108,6 +108,7 @@ struct rlca_policy {
     float *Wimg;     // pre-swizzled tf32 hi/lo image of the conv weights for the tensor-core conv tower
     float *WimgB;    // same for the backward kernel (per tower: conv1 weights | conv2 weights regrouped by tap)
     int conv_bwd_dirty;
+    cudaEvent_t fc_grads_event;   // optional: recorded by rlca_policy_backward once every gradient outside the conv towers is final
     int64_t launches;
 };
 
@@ -1110,6 +1111,13 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
 
 extern "C" int64_t rlca_policy_launch_count(const rlca_policy *p) { return p ? p->launches : -1; }
 
+extern "C" int rlca_policy_set_grad_event(rlca_policy *pol, void *event)
+{
+    if (!pol) return rlca_set_err(RLCA_ERR_INVALID, "NULL workspace");
+    pol->fc_grads_event = (cudaEvent_t)event;
+    return RLCA_OK;
+}
+
 extern "C" int rlca_policy_weights_changed(rlca_policy *p)
 {
     if (!p) return rlca_set_err(RLCA_ERR_INVALID, "policy is NULL");
@@ -1317,6 +1325,9 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
             rlca_tc_transpose_split(fsrc[t], nb, FEAT, FEAT, fth[t], ftl[t], (int)BP, s);
         int rc = rlca_tc_gemm(pw, 2, 256, FEAT, nb, FEAT, 1, 0, s);
         if (rc) return rc;
+        // every gradient outside the conv towers (97 % of the buffer) is final here: a data-parallel caller starts their
+        // all-reduce now, under the dF GEMM and the conv tower backward that follow
+        if (pol->fc_grads_event) RLCA_CUDA_TRY(cudaEventRecord(pol->fc_grads_event, s));
         rc = rlca_tc_gemm(pf, 2, nb, FEAT, 256, FEAT, 1, 0, s);
         if (rc) return rc;
         pol->launches += 5;
@@ -1326,6 +1337,7 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     g.pr[0] = GemmProblem{pol->dX, pol->F, nullptr, nullptr, ga.fc1w};
     g.pr[1] = GemmProblem{pol->dX + B * XLD, pol->F + B * FEAT, nullptr, nullptr, gc.fc1w};
     launch_gemm<true, false>(g, 2, s);
+    if (pol->fc_grads_event) RLCA_CUDA_TRY(cudaEventRecord(pol->fc_grads_event, s));
     // dF (nb x 4096) = dZ1 W_fc1, masked by relu(conv2)
     g.M = nb; g.N = FEAT; g.K = 256; g.lda = XLD; g.ldb = FEAT; g.ldc = FEAT; g.relu = 0;
     g.pr[0] = GemmProblem{pol->dX, ta.fc1w, nullptr, pol->F, pol->dF};

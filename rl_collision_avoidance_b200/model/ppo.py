@@ -142,7 +142,12 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
     if process_group is not None:
         import torch.distributed as dist
         world = dist.get_world_size(group)
-    from ..parallel import average_gradients, plan_minibatches
+    from ..parallel import OverlappedGradSync, plan_minibatches
+    sync = None
+    if process_group is not None:
+        sync = getattr(policy, '_grad_sync', None)
+        if sync is None or sync.group is not group:
+            sync = policy._grad_sync = OverlappedGradSync(policy, group)
     bs = batch_size
     nbatches, sizes, weights = plan_minibatches(n, bs, drop_last, group, distributed=process_group is not None)
     b_obs = torch.empty(bs, frames * obs_size, device=dev)
@@ -180,8 +185,10 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
                 _lib.check(lib.rlca_policy_backward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(policy.grad), st))
             else:
                 policy.grad.zero_()             # this rank ran out of rows: it still takes part in the all-reduce
-            if process_group is not None:
-                average_gradients(policy.grad, group)
+                if sync is not None:
+                    sync.mark_ready()
+            if sync is not None:
+                sync.reduce()                   # fc-side ranges overlap the dF GEMM + conv tower backward
             optimizer.step(grad_scale=1.0 / world)
             k += 1
     rows = log[:k].cpu().tolist()

@@ -94,3 +94,71 @@ def agree_to_stop(local_stop: bool, device=None, group=None) -> bool:
     t = torch.tensor([1.0 if local_stop else 0.0], device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return bool(t.item() > 0)
+
+
+def grad_buckets(offsets):
+    """(early, late) index ranges of the flat gradient buffer.  early = everything outside the conv towers (tensors
+    5..12 and 17..22 of the state_dict order: fc1, fc2, heads - 97 % of the floats), final before the conv tower
+    backward starts; late = logstd + the four conv tensors of each tower."""
+    early = [(offsets[5], offsets[13]), (offsets[17], offsets[23])]
+    late = [(offsets[0], offsets[5]), (offsets[13], offsets[17])]
+    return early, late
+
+
+class OverlappedGradSync:
+    """All-reduce of the flat gradient that hides most of the transfer under the backward pass: librlca records an
+    event when the fc-side gradients are final (rlca_policy_set_grad_event); their ranges are all-reduced from a side
+    stream while the dF GEMM and the conv tower backward still run, the small conv ranges afterwards.  Results are
+    those of one all-reduce of the whole buffer (sum; the 1/world_size goes into the fused Adam step)."""
+
+    def __init__(self, policy, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.policy = policy
+        self.early, self.late = grad_buckets(policy.offsets)
+        self.cuda = policy.grad.is_cuda
+        if self.cuda:
+            from . import _lib
+            import ctypes as C
+            self.side = torch.cuda.Stream(device=policy.device)
+            self.event = torch.cuda.Event(enable_timing=False)
+            self.event.record(torch.cuda.current_stream(policy.device))       # creates the underlying cudaEvent_t
+            self._handle = C.c_void_p(self.event.cuda_event)
+            self._lib = _lib
+            self.attach()
+
+    def attach(self):
+        """(Re-)register the event with the policy's current workspace (a workspace is rebuilt when max_batch grows)."""
+        if self.cuda:
+            self._ws = self.policy._workspace(1)
+            self._lib.check(self.policy.lib.rlca_policy_set_grad_event(self._ws, self._handle))
+
+    def reduce(self):
+        """Call right after rlca_policy_backward on the current stream; returns when the current stream is ordered after
+        every all-reduce."""
+        g = self.policy.grad
+        if not self.cuda:
+            for a, b in self.early + self.late:
+                self.dist.all_reduce(g[a:b], group=self.group)
+            return
+        if self.policy._ws is not self._ws:
+            self.attach()
+        main = torch.cuda.current_stream(g.device)
+        self.side.wait_event(self.event)
+        with torch.cuda.stream(self.side):
+            works = [self.dist.all_reduce(g[a:b], group=self.group, async_op=True) for a, b in self.early]
+        for a, b in self.late:
+            self.dist.all_reduce(g[a:b], group=self.group)
+        for w in works:
+            w.wait()
+        main.wait_stream(self.side)
+
+    def mark_ready(self):
+        """The whole buffer is final on the current stream without a backward pass (e.g. zeroed for an empty minibatch)."""
+        if self.cuda:
+            self.event.record(torch.cuda.current_stream(self.policy.grad.device))
+
+    def close(self):
+        if self.cuda:
+            self._lib.check(self.policy.lib.rlca_policy_set_grad_event(self.policy._workspace(1), None))

@@ -128,3 +128,20 @@ def test_world_size_2_different_row_counts_same_collective_count():
     assert a[True][3] == [16, 16] and b[True][3] == [16, 16]
     assert a[False][:3] == (5, 5, True) and b[False][:3] == (5, 5, True)         # max(ceil(70/16), ceil(41/16))
     assert a[False][3] == [16, 16, 16, 16, 6] and b[False][3] == [16, 16, 9, 0, 0]
+
+
+def test_grad_buckets_cover_the_flat_buffer_once():
+    from rl_collision_avoidance_b200.parallel import grad_buckets
+    # offsets as rlca_policy_param_offset lays them out: tensor starts padded to 32 floats, state_dict order
+    sizes = [2, 480, 32, 3072, 32, 256 * 4096, 256, 128 * 260, 128, 128, 1, 128, 1,
+             480, 32, 3072, 32, 256 * 4096, 256, 128 * 260, 128, 128, 1]
+    off = [0]
+    for n in sizes:
+        off.append(off[-1] + (n + 31) // 32 * 32)
+    early, late = grad_buckets(off)
+    spans = sorted(early + late)
+    assert spans[0][0] == 0 and spans[-1][1] == off[-1]
+    assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))           # contiguous, no overlap
+    assert sum(b - a for a, b in early) > 0.95 * off[-1]                     # the early ranges are the bulk
+    for i in (1, 2, 3, 4, 13, 14, 15, 16):                                   # every conv tensor is in a late range
+        assert any(a <= off[i] and off[i + 1] <= b for a, b in late)
