@@ -8,7 +8,7 @@ lidar + reward/done + obs) over the per-GPU agent batch: 171 stage-1 worlds x 24
 data-path collective (worlds are independent).
 
   value        whole-job agent-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks; the ticks are
-               replayed from a CUDA graph (the launch-bound inner loop of a rollout), one kernel per tick
+               replayed from a CUDA graph (the launch-bound inner loop of a rollout), two kernels per tick
   e2e          same metric through the host-buffer C-ABI call rlca_env_step_host (pinned host buffers in and out,
                PCIe traffic and a stream sync inside every call) — the reference-facing call
   roofline     algorithmic bytes (4*B+96 per agent-step) / measured per-tick time vs the measured
@@ -564,11 +564,14 @@ def main():
         tick(i)
     sync()
     graph = None
+    launches_per_graph = 0
     if G:
         graph = torch.cuda.CUDAGraph()
+        lg = env.launch_count
         with torch.cuda.graph(graph):
             for i in range(G):
                 tick(i)
+        launches_per_graph = env.launch_count - lg      # kernels captured: physics + lidar per tick
         graph.replay()                                   # untimed: uploads the graph
     sync()
     sampler = ClockSampler(local_rank)
@@ -587,7 +590,7 @@ def main():
     e1.record()
     sync()
     ms = e0.elapsed_time(e1)
-    launches = args.steps if graph is not None else env.launch_count - l0      # one kernel per tick either way
+    launches = (args.steps // G) * launches_per_graph if graph is not None else env.launch_count - l0
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -655,7 +658,7 @@ def main():
                        'agents_per_gpu': N, 'beams': BEAMS, 'parallelism': f'worlds sharded over {world_size} GPU(s), '
                        'no data-path collective',
                        'l2': 'obs written round-robin into a 128-slot rollout ring (1.08 GB > 126 MB L2)',
-                       'launch': (f'CUDA graph of {G} consecutive ticks replayed {args.steps // G}x (one kernel per tick)'
+                       'launch': (f'CUDA graph of {G} consecutive ticks replayed {args.steps // G}x ({launches_per_graph // max(G, 1)} kernels per tick: physics, lidar)'
                                   if graph is not None else 'one rlca_env_step call per tick from Python'),
                        'ctas_per_world': args.ctas_per_world or 'auto'},
             'roofline': {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
