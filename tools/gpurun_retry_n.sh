@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage: tools/gpurun_retry_n.sh <gpus> <timeout_s> <logfile> <command...>
+G=$1; T=$2; LOG=$3; shift 3
+for i in $(seq 1 30); do
+  /usr/local/graft/bin/gpurun --gpus "$G" --timeout "$T" -- "$@" > "$LOG" 2>&1
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 90
+done
+exit 3
