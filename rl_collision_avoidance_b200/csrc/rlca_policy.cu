@@ -109,6 +109,7 @@ struct rlca_policy {
     float *WimgB;    // same for the backward kernel (per tower: conv1 weights | conv2 weights regrouped by tap)
     int conv_bwd_dirty;
     cudaEvent_t fc_grads_event;   // optional: recorded by rlca_policy_backward once every gradient outside the conv towers is final
+    int reserved_sms;             // SMs the persistent conv tower backward leaves free while that event is set (for the collective)
     int64_t launches;
 };
 
@@ -1115,6 +1116,10 @@ extern "C" int rlca_policy_set_grad_event(rlca_policy *pol, void *event)
 {
     if (!pol) return rlca_set_err(RLCA_ERR_INVALID, "NULL workspace");
     pol->fc_grads_event = (cudaEvent_t)event;
+    // The conv tower backward is a persistent kernel whose CTAs fill every SM's shared memory: an NCCL kernel launched
+    // meanwhile would only start when it ends.  While a gradient event is set it runs on 16 SMs fewer (measured at
+    // N = 2: the 46 us all-reduce then hides under the 147 us of dF GEMM + conv backward instead of following them).
+    pol->reserved_sms = event ? 16 : 0;
     return RLCA_OK;
 }
 
@@ -1353,10 +1358,11 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
             pol->conv_bwd_dirty = 0;
             pol->launches += 1;
         }
-        int rc = rlca_conv_tc_backward(obs, pol->WimgB, pol->dF, pol->F, pol->part, nb, pol->num_sms, s);
+        const int bwd_sms = pol->num_sms - pol->reserved_sms > 8 ? pol->num_sms - pol->reserved_sms : pol->num_sms;
+        int rc = rlca_conv_tc_backward(obs, pol->WimgB, pol->dF, pol->F, pol->part, nb, bwd_sms, s);
         if (rc) return rc;
         conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(
-            pol->part, rlca_conv_tc_bwd_slots(nb, pol->num_sms), pol->S);
+            pol->part, rlca_conv_tc_bwd_slots(nb, bwd_sms), pol->S);
     } else {
         conv_tower_bwd_kernel<<<dim3((nb + CONV_SPC - 1) / CONV_SPC, 2), 256, sizeof(ConvBwdSmem), s>>>(
             obs, pol->Wc, ta, tc, pol->dF, pol->use_tc ? pol->F : nullptr, pol->part, nb);

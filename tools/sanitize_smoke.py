@@ -26,9 +26,6 @@ def main():
             env.step_host(a_host)
         torch.cuda.synchronize()
         env.close()
-    if '--env-only' in sys.argv:
-        print('sanitize workload done (env only)')
-        return
     if '--circle' in sys.argv:
         env = StageWorld(512, scenario='circle', num_worlds=1, seed=1, auto_reset=1)
         env.reset_pose()
@@ -36,6 +33,9 @@ def main():
             env.control_vel(torch.rand(env.N, 2, device='cuda'))
         torch.cuda.synchronize()
         env.close()
+    if '--env-only' in sys.argv:
+        print('sanitize workload done (env only)')
+        return
     for tc in (True, False):
         pol = CNNPolicy(max_batch=64)
         pol.set_tensor_cores(tc)
