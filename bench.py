@@ -345,9 +345,22 @@ def section_tick(torch, dev, scenario, worlds, auto_reset, cores, n=200):
     acts = [torch.from_numpy(random_actions(rng, env.N)).to(dev) for _ in range(16)]
     slots = max(2, int(300e6 / (env.N * BEAMS * 4)) + 1)
     ring = torch.empty(slots, env.N, BEAMS, device=dev)
+    def tick(i):
+        env.control_vel(acts[i % 16], obs_out=ring[i % slots])
+    for i in range(10):
+        tick(i)
+    torch.cuda.synchronize(dev)
+    # like the headline region: the ticks are replayed from a CUDA graph (G even: the state ping-pong closes)
+    G = 2 * max(1, min(n, 2 * slots) // 2)
+    graph = torch.cuda.CUDAGraph()
     l0 = env.launch_count
-    ms = gpu_time(torch, dev, lambda i: env.control_vel(acts[i % 16], obs_out=ring[i % slots]), n, warm=10)
-    launches = (env.launch_count - l0) / (n + 10)
+    with torch.cuda.graph(graph):
+        for i in range(G):
+            tick(i)
+    launches = (env.launch_count - l0) / G
+    graph.replay()
+    reps = max(1, n // G)
+    ms = gpu_time(torch, dev, lambda i: graph.replay(), reps, warm=1) / G
     N = env.N
     env.close()
     del env, ring
