@@ -8,6 +8,7 @@
 // Parameters, gradients and Adam moments are flat fp32 buffers in state_dict order (tensor starts
 // padded to 32 floats so every matrix is 128-byte aligned).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -1120,6 +1121,7 @@ extern "C" int rlca_policy_set_grad_event(rlca_policy *pol, void *event)
     // meanwhile would only start when it ends.  While a gradient event is set it runs on 16 SMs fewer (measured at
     // N = 2: the 46 us all-reduce then hides under the 147 us of dF GEMM + conv backward instead of following them).
     pol->reserved_sms = event ? 16 : 0;
+    if (event) { const char *e = getenv("RLCA_RESERVED_SMS"); if (e) pol->reserved_sms = atoi(e); }     // experiment knob
     return RLCA_OK;
 }
 
