@@ -476,18 +476,44 @@ def section_learner_dp(torch, dist, dev, world_size):
         dist.all_reduce(pol.grad)
 
     res = {}
-    for k, fn in (('step_us', full), ('step_serial_allreduce_us', serial), ('step_without_allreduce_us', local),
-                  ('allreduce_alone_us', ar)):
+    variants = [('step_overlapped_allreduce_us', full), ('step_serial_allreduce_us', serial),
+                ('step_without_allreduce_us', local), ('allreduce_alone_us', ar)]
+    for k, fn in variants:
         ms = gpu_time(torch, dev, fn, 20, warm=5)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res[k] = float(t.item()) * 1e3
+    sync.close()
+    # the product path: gradient sum + Adam + broadcast as ONE kernel over NVLink peer memory (parallel.PeerAdam)
+    try:
+        from rl_collision_avoidance_b200.parallel import PeerAdam
+        peer = PeerAdam.attach(pol, opt)
+
+        def fused(_=0):
+            compute()
+            opt.step(grad_scale=1.0 / world_size)
+
+        def fused_alone(_=0):
+            opt.step(grad_scale=1.0 / world_size)
+        for k, fn in (('step_us', fused), ('peer_adam_alone_us', fused_alone)):
+            ms = gpu_time(torch, dev, fn, 20, warm=5)
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[k] = float(t.item()) * 1e3
+        res['path'] = 'peer memory, ' + ('NVLS multicast (multimem.ld_reduce / multimem.st)' if peer.nvls else 'P2P loads / stores')
+    except Exception as e:
+        res['peer_error'] = repr(e)
+        res['step_us'] = res['step_serial_allreduce_us']
+        res['path'] = 'NCCL all-reduce + Adam'
     res['allreduce_bytes'] = int(pol.flat_size * 4)
-    res['allreduce_share'] = max(0.0, res['step_us'] - res['step_without_allreduce_us']) / res['step_us']
+    res['collective_share'] = max(0.0, res['step_us'] - res['step_without_allreduce_us']) / res['step_us']
+    res['efficiency_vs_no_collective'] = res['step_without_allreduce_us'] / res['step_us']
     res['samples_per_s'] = nb * world_size / (res['step_us'] * 1e-6)
     res['batch_per_rank'] = nb
-    res['how'] = ('step_us: fc-side gradient ranges (97 % of 8.69 MB) all-reduced from a side stream once '
-                  'rlca_policy_backward signals them, under the dF GEMM and the conv tower backward; conv ranges after')
+    res['how'] = ('step_us: forward + loss + backward + ONE kernel that sums the gradient over the ranks, applies Adam and '
+                  'writes parameter and moments into every rank (reduce-scatter + Adam + all-gather over peer memory); '
+                  'step_serial: NCCL all-reduce of the 8.69 MB buffer + Adam; step_overlapped: fc-side ranges all-reduced '
+                  'from a side stream under the rest of the backward')
     return res
 
 

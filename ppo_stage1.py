@@ -82,6 +82,16 @@ def main(stage=1, world_cls=StageWorld, num_env=NUM_ENV, batch_size=BATCH_SIZE, 
     policy = CNNPolicy(frames=LASER_HIST, action_space=2, device=device, seed=args.seed, max_batch=max(batch_size, env.N))
     policy.sample_seed = args.seed * 1000003 + rank              # every rank draws its own action noise
     opt = Adam(policy.parameters(), lr=LEARNING_RATE)
+    if world_size > 1 and os.environ.get('RLCA_DP_PEER', '1') == '1':
+        # gradient sum + Adam + broadcast as one kernel over NVLink peer memory; NCCL all-reduce + Adam otherwise
+        try:
+            from rl_collision_avoidance_b200.parallel import PeerAdam
+            peer = PeerAdam.attach(policy, opt)
+            if logger:
+                logger.info('data-parallel optimizer step over peer memory (%s)' % ('NVLS multicast' if peer.nvls else 'P2P'))
+        except Exception as e:                      # no symmetric memory on this box: the NCCL path is always there
+            if logger:
+                logger.info('peer-memory optimizer step unavailable (%r): NCCL all-reduce + Adam' % (e,))
     os.makedirs(args.policy_path, exist_ok=True)
     file = args.policy_path + '/' + ckpt
     if os.path.exists(file):

@@ -88,6 +88,18 @@ class CNNPolicy:
             v.copy_(((torch.rand(shape, generator=gen) * 2 - 1) * bound).to(self.device))
         self.weights_changed()
 
+    def rebind_storage(self, flat, grad):
+        """Move the flat parameter / gradient buffers into caller-provided storage (e.g. a symmetric-memory allocation
+        that the other ranks can address); contents are copied, the named views are rebuilt."""
+        flat.copy_(self.flat)
+        grad.copy_(self.grad)
+        self.flat, self.grad = flat, grad
+        for i, (name, shape) in enumerate(TENSORS):
+            n = math.prod(shape)
+            self.views[name] = self.flat[self.offsets[i]:self.offsets[i] + n].view(shape)
+            self.grad_views[name] = self.grad[self.offsets[i]:self.offsets[i] + n].view(shape)
+        self.weights_changed()
+
     def weights_changed(self):
         """Call after writing to the parameter buffer outside Adam.step / load_state_dict."""
         if getattr(self, '_ws', None) is not None:
@@ -222,6 +234,7 @@ class Adam:
         self.exp_avg = torch.zeros_like(policy.flat)
         self.exp_avg_sq = torch.zeros_like(policy.flat)
         self.step_count = 0
+        self.peer = None          # data-parallel run: the fused all-reduce + Adam over peer memory (parallel.PeerAdam)
 
     def zero_grad(self):
         self.policy.grad.zero_()
@@ -229,6 +242,10 @@ class Adam:
     def step(self, grad_scale=1.0):
         p = self.policy
         self.step_count += 1
+        if self.peer is not None:           # gradient sum over the ranks, Adam and the broadcast of the result: one kernel
+            self.peer.step(self, grad_scale)
+            p.weights_changed()
+            return
         _lib.check(p.lib.rlca_adam_step(_ptr(p.flat), _ptr(p.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                         p.flat_size, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
                                         grad_scale, p._stream()))

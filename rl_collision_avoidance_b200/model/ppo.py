@@ -142,9 +142,14 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
     if process_group is not None:
         import torch.distributed as dist
         world = dist.get_world_size(group)
-    from ..parallel import OverlappedGradSync, plan_minibatches
+    from ..parallel import OverlappedGradSync, average_gradients, plan_minibatches
+    # gradient exchange of a data-parallel run, in order of preference: (1) optimizer.peer (parallel.PeerAdam): the sum
+    # over the ranks is part of the fused Adam kernel, nothing to do here; (2) one NCCL all-reduce of the flat buffer
+    # after the backward; (3) RLCA_DP_OVERLAP=1: the fc-side ranges all-reduced under the rest of the backward
+    # (parallel.OverlappedGradSync - no gain measured at N = 2 with NCCL's default channel count)
     sync = None
-    if process_group is not None:
+    peer = getattr(optimizer, 'peer', None) is not None
+    if process_group is not None and not peer and os.environ.get('RLCA_DP_OVERLAP', '0') == '1':
         sync = getattr(policy, '_grad_sync', None)
         if sync is None or sync.group is not group:
             sync = policy._grad_sync = OverlappedGradSync(policy, group)
@@ -189,6 +194,8 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
                     sync.mark_ready()
             if sync is not None:
                 sync.reduce()                   # fc-side ranges overlap the dF GEMM + conv tower backward
+            elif process_group is not None and not peer:
+                average_gradients(policy.grad, group)
             optimizer.step(grad_scale=1.0 / world)
             k += 1
     rows = log[:k].cpu().tolist()

@@ -162,3 +162,66 @@ class OverlappedGradSync:
     def close(self):
         if self.cuda:
             self._lib.check(self.policy.lib.rlca_policy_set_grad_event(self.policy._workspace(1), None))
+
+
+class PeerAdam:
+    """Data-parallel optimizer step as ONE kernel over NVLink peer memory (csrc/rlca_dp.cu): reduce-scatter of the flat
+    gradient + Adam + all-gather of the parameter and both moments, instead of an NCCL all-reduce followed by the Adam
+    kernel (the reference takes an optimizer step per minibatch, model/ppo.py:186-188, so the collective is on the
+    critical path of every step).  The four flat buffers of the policy / optimizer move into one symmetric-memory
+    allocation (torch.distributed._symmetric_memory: peer mappings of every rank's buffer, the NVSwitch multicast
+    mapping when the fabric offers one, and cross-GPU barriers); rank r updates shard r and writes it into every rank's
+    buffers, so weights and optimizer state stay replicated bit for bit and checkpoints need no gather.
+
+        opt = Adam(policy.parameters(), lr)
+        PeerAdam.attach(policy, opt)          # after init_process_group('nccl'); raises if peer memory is unavailable
+        ... backward ...; opt.step(grad_scale=1 / world)     # no separate gradient all-reduce
+    """
+
+    def __init__(self, policy, optimizer, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib, self._C = _lib, C
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        n = policy.flat_size
+        if n % 4:
+            raise ValueError('flat buffer size must be a multiple of 4 floats')
+        self.n = n
+        self.buf = symm_mem.empty(4 * n, dtype=torch.float32, device=policy.device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        grad, flat = self.buf[0:n], self.buf[n:2 * n]
+        m, v = self.buf[2 * n:3 * n], self.buf[3 * n:4 * n]
+        m.copy_(optimizer.exp_avg)
+        v.copy_(optimizer.exp_avg_sq)
+        policy.rebind_storage(flat, grad)
+        optimizer.exp_avg, optimizer.exp_avg_sq = m, v
+        base = [int(x) for x in self.hdl.buffer_ptrs]
+        arr = C.c_uint64 * self.world
+        self._grad = arr(*[b for b in base])
+        self._param = arr(*[b + 4 * n for b in base])
+        self._m = arr(*[b + 8 * n for b in base])
+        self._v = arr(*[b + 12 * n for b in base])
+        mc = int(getattr(self.hdl, 'multicast_ptr', 0) or 0)
+        self.nvls = mc != 0
+        self._mc = [mc + k * 4 * n if mc else 0 for k in range(4)]
+        self.policy = policy
+        torch.cuda.synchronize(policy.device)
+        self.hdl.barrier(channel=0)                      # everybody's buffers are in place before anybody steps
+
+    @classmethod
+    def attach(cls, policy, optimizer, group=None):
+        optimizer.peer = cls(policy, optimizer, group)
+        return optimizer.peer
+
+    def step(self, opt, grad_scale):
+        p = self.policy
+        self.hdl.barrier(channel=0)                      # every rank's gradient is complete
+        self._lib.check(p.lib.rlca_adam_step_allreduce(
+            self._grad, self._param, self._m, self._v, self._mc[0], self._mc[1], self._mc[2], self._mc[3],
+            self.rank, self.world, self.n, opt.lr, opt.betas[0], opt.betas[1], opt.eps, opt.step_count, grad_scale,
+            p._stream()))
+        self.hdl.barrier(channel=1)                      # every shard has landed everywhere
