@@ -495,7 +495,18 @@ def section_learner_dp(torch, dist, dev, world_size):
 
         def fused_alone(_=0):
             opt.step(grad_scale=1.0 / world_size)
-        for k, fn in (('step_us', fused), ('peer_adam_alone_us', fused_alone)):
+        def barriers(_=0):
+            peer.hdl.barrier(channel=0)
+            peer.hdl.barrier(channel=1)
+
+        def kernel_only(_=0):          # timing only: the two barriers of a real step are what makes it safe
+            opt.step_count += 1
+            _lib.check(lib.rlca_adam_step_allreduce(peer._grad, peer._param, peer._m, peer._v, peer._mc[0], peer._mc[1],
+                                                    peer._mc[2], peer._mc[3], peer.rank, peer.world, peer.n, opt.lr,
+                                                    opt.betas[0], opt.betas[1], opt.eps, opt.step_count,
+                                                    1.0 / world_size, 0, st))
+        for k, fn in (('step_us', fused), ('peer_adam_alone_us', fused_alone), ('peer_barriers_alone_us', barriers),
+                      ('peer_kernel_alone_us', kernel_only)):
             ms = gpu_time(torch, dev, fn, 20, warm=5)
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

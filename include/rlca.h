@@ -244,14 +244,15 @@ int rlca_policy_set_grad_event(rlca_policy *pol, void *event);
  * device addresses: the peer mappings of every rank's flat gradient / parameter / exp_avg / exp_avg_sq buffer (n floats
  * each, n % 4 == 0), e.g. from a symmetric-memory allocation; mc_* are the NVSwitch multicast mappings of the same
  * buffers (NVLS: multimem.ld_reduce / multimem.st) or 0 to use plain peer loads and stores.  Rank r updates elements
- * [r * ceil(n / world), ...) and writes them into every rank's buffers, so parameters and optimizer state stay
- * replicated bit for bit.  The caller puts a cross-GPU barrier before (all gradients written) and after (all shards
- * written) the call.  Same arithmetic as rlca_adam_step with grad_scale = 1 / world on the summed gradient
+ * [r * ceil(n / world), ...): the new parameters go into every rank's buffer (replicated bit for bit), the two
+ * moments stay in the owner's buffer (sharded optimizer state; a checkpoint reads the shards back through the peer
+ * mappings) unless replicate_moments != 0.  The caller puts a cross-GPU barrier before (all gradients written) and
+ * after (all shards written) the call.  Same arithmetic as rlca_adam_step with grad_scale = 1 / world on the summed gradient
  * (model/ppo.py:186-188 + ppo_stage1.py:179 at any world size). */
 int rlca_adam_step_allreduce(const uint64_t *grad_ptrs, const uint64_t *param_ptrs, const uint64_t *m_ptrs,
                              const uint64_t *v_ptrs, uint64_t mc_grad, uint64_t mc_param, uint64_t mc_m, uint64_t mc_v,
                              int32_t rank, int32_t world, int64_t n, float lr, float beta1, float beta2, float eps,
-                             int32_t step, float grad_scale, void *stream);
+                             int32_t step, float grad_scale, int32_t replicate_moments, void *stream);
 /* Conv tower + fc1 forward/backward GEMMs on the tcgen05 tensor cores with 3xTF32 error compensation
  * (enable = 1, the default); 2 = fc1 GEMMs only; 0 selects the plain fp32 CUDA-core kernels (kept as the
  * cross-check for the tensor-core path). */

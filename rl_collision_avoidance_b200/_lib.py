@@ -75,7 +75,7 @@ SYMBOLS = {
     'rlca_policy_launch_count': (C.c_int64, [_P]),
     'rlca_policy_set_grad_event': (C.c_int, [_P, _P]),
     'rlca_adam_step_allreduce': (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32,
-                                           C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_float, _P]),
+                                           C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_int32, _P]),
     'rlca_policy_set_tensor_cores': (C.c_int, [_P, C.c_int32]),
     'rlca_policy_weights_changed': (C.c_int, [_P]),
     'rlca_policy_features': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),

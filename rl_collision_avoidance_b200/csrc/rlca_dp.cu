@@ -8,10 +8,12 @@
 //     sums the gradient over all ranks   - plain loads from the W peer mappings, or one multimem.ld_reduce.add on the
 //                                          NVSwitch multicast mapping (the switch does the sum in flight, NVLS);
 //     applies Adam                       - same arithmetic and rounding as adam_kernel (torch.optim.Adam semantics);
-//     writes the new parameter and both moments into EVERY rank's buffers - W peer stores, or one multimem.st each.
+//     writes the new parameter into EVERY rank's buffer - W peer stores, or one multimem.st (the switch replicates it);
+//     keeps the two moments of its shard locally (the optimizer state is sharded: a checkpoint reads the shards back
+//     through the peer mappings), or - replicate_moments - writes them everywhere too (3x the outbound traffic).
 //
-// Every rank therefore ends with bit-identical parameters and optimizer state (replicated, so checkpoints need no
-// gather), having moved 1/W of the gradient in and 3/W of the state out per peer.  The caller brackets the launch with
+// Every rank therefore ends with bit-identical parameters, having moved 1/W of the gradient in and 1/W of the
+// parameters out per peer.  The caller brackets the launch with
 // two cross-GPU barriers (all gradients complete before / all shards written after); buffers and barriers come from a
 // symmetric-memory allocation (PyTorch's, which is plumbing here: cuMemCreate + peer mapping + multicast binding).
 #include <cuda_runtime.h>
@@ -48,7 +50,7 @@ __device__ __forceinline__ void mm_st(float *p, float4 v)
                  : "memory");
 }
 
-template <bool NVLS>
+template <bool NVLS, bool REPL>
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_constant__ DpPtrs P, int rank, int world,
                                                              int64_t lo, int64_t hi, float lr, float b1, float b2,
                                                              float eps, float bc1, float bc2_sqrt, float grad_scale)
@@ -85,14 +87,19 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
                      np = make_float4(pi[0], pi[1], pi[2], pi[3]);
         if (NVLS) {
             mm_st(P.mc_param + i, np);
-            mm_st(P.mc_m + i, nm);
-            mm_st(P.mc_v + i, nv);
+            if (REPL) { mm_st(P.mc_m + i, nm); mm_st(P.mc_v + i, nv); }
         } else {
             for (int q = 0; q < world; ++q) {
                 *reinterpret_cast<float4 *>(P.param[q] + i) = np;
-                *reinterpret_cast<float4 *>(P.m[q] + i) = nm;
-                *reinterpret_cast<float4 *>(P.v[q] + i) = nv;
+                if (REPL) {
+                    *reinterpret_cast<float4 *>(P.m[q] + i) = nm;
+                    *reinterpret_cast<float4 *>(P.v[q] + i) = nv;
+                }
             }
+        }
+        if (!REPL) {
+            *reinterpret_cast<float4 *>(P.m[rank] + i) = nm;
+            *reinterpret_cast<float4 *>(P.v[rank] + i) = nv;
         }
     }
 }
@@ -100,7 +107,8 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(const __grid_consta
 extern "C" int rlca_adam_step_allreduce(const uint64_t *grad_ptrs, const uint64_t *param_ptrs, const uint64_t *m_ptrs,
                                         const uint64_t *v_ptrs, uint64_t mc_grad, uint64_t mc_param, uint64_t mc_m,
                                         uint64_t mc_v, int32_t rank, int32_t world, int64_t n, float lr, float beta1,
-                                        float beta2, float eps, int32_t step, float grad_scale, void *stream)
+                                        float beta2, float eps, int32_t step, float grad_scale, int32_t replicate_moments,
+                                        void *stream)
 {
     if (!grad_ptrs || !param_ptrs || !m_ptrs || !v_ptrs || world < 1 || world > DP_MAX_RANKS || rank < 0 || rank >= world ||
         n < 1 || (n & 3) || step < 1)
@@ -128,12 +136,13 @@ extern "C" int rlca_adam_step_allreduce(const uint64_t *grad_ptrs, const uint64_
         const int64_t n4 = (hi - lo) >> 2;
         unsigned blocks = (unsigned)((n4 + 255) / 256);
         if (blocks > 592u) blocks = 592u;                       // 4 CTAs per SM: the kernel is bound by the links
-        if (nvls)
-            adam_allreduce_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, rank, world, lo, hi, lr, beta1, beta2, eps,
-                                                                                 bc1, sqrtf(bc2), grad_scale);
-        else
-            adam_allreduce_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(P, rank, world, lo, hi, lr, beta1, beta2,
-                                                                                  eps, bc1, sqrtf(bc2), grad_scale);
+#define DP_LAUNCH(NV, RP) adam_allreduce_kernel<NV, RP><<<blocks, 256, 0, (cudaStream_t)stream>>>( \
+            P, rank, world, lo, hi, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale)
+        if (nvls && replicate_moments) DP_LAUNCH(true, true);
+        else if (nvls) DP_LAUNCH(true, false);
+        else if (replicate_moments) DP_LAUNCH(false, true);
+        else DP_LAUNCH(false, false);
+#undef DP_LAUNCH
         RLCA_CUDA_TRY(cudaGetLastError());
     }
     return RLCA_OK;

@@ -252,8 +252,11 @@ class Adam:
         p.weights_changed()
 
     def state_dict(self):
-        return {'exp_avg': self.exp_avg.clone(), 'exp_avg_sq': self.exp_avg_sq.clone(), 'step': self.step_count,
-                'lr': self.lr, 'betas': self.betas, 'eps': self.eps}
+        if self.peer is not None:           # sharded moments: read the other ranks' shards through the peer mappings
+            m, v = self.peer.gather_moments()
+        else:
+            m, v = self.exp_avg.clone(), self.exp_avg_sq.clone()
+        return {'exp_avg': m, 'exp_avg_sq': v, 'step': self.step_count, 'lr': self.lr, 'betas': self.betas, 'eps': self.eps}
 
     def load_state_dict(self, sd):
         self.exp_avg.copy_(sd['exp_avg'])

@@ -170,18 +170,21 @@ class PeerAdam:
     kernel (the reference takes an optimizer step per minibatch, model/ppo.py:186-188, so the collective is on the
     critical path of every step).  The four flat buffers of the policy / optimizer move into one symmetric-memory
     allocation (torch.distributed._symmetric_memory: peer mappings of every rank's buffer, the NVSwitch multicast
-    mapping when the fabric offers one, and cross-GPU barriers); rank r updates shard r and writes it into every rank's
-    buffers, so weights and optimizer state stay replicated bit for bit and checkpoints need no gather.
+    mapping when the fabric offers one, and cross-GPU barriers); rank r updates shard r and writes the new parameters
+    into every rank's buffer, so the weights stay replicated bit for bit.  The Adam moments are sharded (rank r owns
+    those of shard r; `gather_moments()` reads them back through the peer mappings for a checkpoint) unless
+    `replicate_moments=True`.
 
         opt = Adam(policy.parameters(), lr)
         PeerAdam.attach(policy, opt)          # after init_process_group('nccl'); raises if peer memory is unavailable
         ... backward ...; opt.step(grad_scale=1 / world)     # no separate gradient all-reduce
     """
 
-    def __init__(self, policy, optimizer, group=None):
+    def __init__(self, policy, optimizer, group=None, replicate_moments=False):
         import ctypes as C
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
+        self.replicate = bool(replicate_moments)
         from . import _lib
         self._lib, self._C = _lib, C
         group = group if group is not None else dist.group.WORLD
@@ -213,9 +216,30 @@ class PeerAdam:
         self.hdl.barrier(channel=0)                      # everybody's buffers are in place before anybody steps
 
     @classmethod
-    def attach(cls, policy, optimizer, group=None):
-        optimizer.peer = cls(policy, optimizer, group)
+    def attach(cls, policy, optimizer, group=None, replicate_moments=False):
+        optimizer.peer = cls(policy, optimizer, group, replicate_moments)
         return optimizer.peer
+
+    def shard(self, r):
+        chunk = ((self.n // 4 + self.world - 1) // self.world) * 4
+        lo = min(r * chunk, self.n)
+        return lo, min(lo + chunk, self.n)
+
+    def gather_moments(self):
+        """(exp_avg, exp_avg_sq) of the whole buffer on this rank: every shard read from its owner through the peer
+        mapping (no collective: call it when no optimizer step is in flight, e.g. between updates)."""
+        torch.cuda.synchronize(self.policy.device)
+        n = self.n
+        m, v = self.buf[2 * n:3 * n].clone(), self.buf[3 * n:4 * n].clone()
+        if not self.replicate:
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                lo, hi = self.shard(r)
+                remote = self.hdl.get_buffer(r, (4 * n,), torch.float32)
+                m[lo:hi].copy_(remote[2 * n + lo:2 * n + hi])
+                v[lo:hi].copy_(remote[3 * n + lo:3 * n + hi])
+        return m, v
 
     def step(self, opt, grad_scale):
         p = self.policy
@@ -223,5 +247,5 @@ class PeerAdam:
         self._lib.check(p.lib.rlca_adam_step_allreduce(
             self._grad, self._param, self._m, self._v, self._mc[0], self._mc[1], self._mc[2], self._mc[3],
             self.rank, self.world, self.n, opt.lr, opt.betas[0], opt.betas[1], opt.eps, opt.step_count, grad_scale,
-            p._stream()))
+            int(self.replicate), p._stream()))
         self.hdl.barrier(channel=1)                      # every shard has landed everywhere

@@ -46,11 +46,13 @@ def _worker(rank, world, port, out):
             opt.step(grad_scale=1.0 / world)
             torch.cuda.synchronize(dev)
             # world = 2: a + b is the same float whichever rank (or the switch) adds it -> bit-exact
-            same = torch.equal(pol.flat, p_ref) and torch.equal(opt.exp_avg, m_ref) and torch.equal(opt.exp_avg_sq, v_ref)
-            close = (pol.flat - p_ref).abs().max().item() < 1e-6 and (opt.exp_avg - m_ref).abs().max().item() < 1e-6
+            gm, gv = opt.state_dict()['exp_avg'], opt.state_dict()['exp_avg_sq']      # sharded moments, gathered over P2P
+            same = torch.equal(pol.flat, p_ref) and torch.equal(gm, m_ref) and torch.equal(gv, v_ref)
+            close = (pol.flat - p_ref).abs().max().item() < 1e-6 and (gm - m_ref).abs().max().item() < 1e-6
+            dist.barrier()                        # nobody steps again while a peer is still reading its shard
             ok_vals = ok_vals and (same if world == 2 else close)
             # replicated state: every rank holds the same bits
-            chk = torch.stack([pol.flat.double().sum(), opt.exp_avg.double().sum(), opt.exp_avg_sq.double().sum()])
+            chk = torch.stack([pol.flat.double().sum(), gm.double().sum(), gv.double().sum()])
             lo, hi = chk.clone(), chk.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)

@@ -1,12 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_dp_peer_gpu.py -m gpu -q -s > gpurun_out/r2n_pytest_peer.log 2>&1; echo "exit $?" >> gpurun_out/r2n_pytest_peer.log; tail -15 gpurun_out/r2n_pytest_peer.log
+timeout 600 python -m pytest tests/test_dp_peer_gpu.py -m gpu -q -s > gpurun_out/r2o_pytest_peer.log 2>&1; echo "exit $?" >> gpurun_out/r2o_pytest_peer.log; tail -15 gpurun_out/r2o_pytest_peer.log
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
-    bench.py --gpus 2 --steps 200 --warmup 20 --e2e-steps 5 > gpurun_out/r2n_bench_n2.json 2> gpurun_out/r2n_bench_n2.err
+    bench.py --gpus 2 --steps 200 --warmup 20 --e2e-steps 5 > gpurun_out/r2o_bench_n2.json 2> gpurun_out/r2o_bench_n2.err
 python -c "
 import json
-d=json.loads(open('gpurun_out/r2n_bench_n2.json').read().strip().splitlines()[-1]); print(d['value'], json.dumps(d['learner_dp'], indent=1))"; tail -5 gpurun_out/r2n_bench_n2.err
+d=json.loads(open('gpurun_out/r2o_bench_n2.json').read().strip().splitlines()[-1]); print(d['value'], json.dumps(d['learner_dp'], indent=1))"; tail -5 gpurun_out/r2o_bench_n2.err
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 \
-    ppo_stage2.py --num-worlds 6 --updates 2 --policy-path gpurun_out/r2n_policy > gpurun_out/r2n_train_stage2_n2.log 2>&1
-echo "stage2 dp exit $?" >> gpurun_out/r2n_train_stage2_n2.log; tail -4 gpurun_out/r2n_train_stage2_n2.log; grep -i "peer" log/*/output.log 2>/dev/null | tail -2
-rm -rf gpurun_out/r2n_policy
+    ppo_stage2.py --num-worlds 6 --updates 2 --policy-path gpurun_out/r2o_policy > gpurun_out/r2o_train_stage2_n2.log 2>&1
+echo "stage2 dp exit $?" >> gpurun_out/r2o_train_stage2_n2.log; tail -4 gpurun_out/r2o_train_stage2_n2.log; grep -i "peer" log/*/output.log 2>/dev/null | tail -2
+rm -rf gpurun_out/r2o_policy
