@@ -328,6 +328,13 @@ int rlca_adv_apply(const float *x_dev, int64_t n, const double *moments_dev, flo
 int rlca_gather_rows(const float *src_dev, const int64_t *idx_dev, int32_t row_floats, int32_t nrows, float *dst_dev,
                      void *stream);
 
+/* The same for all arrays of a minibatch in ONE launch (the reference indexes obs, goal, speed, action, logprob, adv,
+ * target with the same sampler index, model/ppo.py:162-169): dst[a][i,:] = src[a][idx[i],:], rows of row_floats[a]
+ * floats, a < narrays <= RLCA_GATHER_MAX.  src / dst / row_floats are HOST arrays of device pointers / sizes. */
+#define RLCA_GATHER_MAX 8
+int rlca_gather_minibatch(const float *const *src_dev, const int32_t *row_floats, int32_t narrays,
+                          const int64_t *idx_dev, int32_t nrows, float *const *dst_dev, void *stream);
+
 /* Observation stack push (the deque of ppo_stage1.py:60,87-89): stack_out[:,0:2] = stack_in[:,1:3],
  * stack_out[:,2] = obs; agents whose flags say was_reset get three copies of obs. */
 int rlca_obs_stack_push(const float *stack_in_dev, const float *obs_dev, const uint8_t *flags_dev, int32_t n,

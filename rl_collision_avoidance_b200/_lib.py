@@ -94,6 +94,7 @@ SYMBOLS = {
     'rlca_adv_moments': (C.c_int, [_P, C.c_int64, _P, _P]),
     'rlca_adv_apply': (C.c_int, [_P, C.c_int64, _P, _P, _P]),
     'rlca_gather_rows': (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    'rlca_gather_minibatch': (C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P, _P]),
     'rlca_obs_stack_push': (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
     'rlca_last_error': (C.c_char_p, []),
     'rlca_version': (C.c_char_p, []),

@@ -111,6 +111,12 @@ struct rlca_policy {
     int conv_bwd_dirty;
     cudaEvent_t fc_grads_event;   // optional: recorded by rlca_policy_backward once every gradient outside the conv towers is final
     int reserved_sms;             // SMs the persistent conv tower backward leaves free while that event is set (for the collective)
+    // ---- side streams of the backward: the work that is not on the chain heads -> dX -> dF -> conv towers (transposed
+    // split of F, every weight / bias gradient of the fc layers and the heads) runs beside it
+    int use_side;                 // 0: one stream (RLCA_BWD_STREAMS=0, or while fc_grads_event is set)
+    cudaStream_t side[2];
+    cudaEvent_t ev_fork, ev_heads, ev_dx, ev_split, ev_join[2];
+    float *S2;                    // split-reduction scratch of the conv tower partials (the side streams use S meanwhile)
     int64_t launches;
 };
 
@@ -501,7 +507,7 @@ __global__ void conv_part_final_kernel(const float *__restrict__ P, int splits, 
 // ------------------------------------------------------------------------------------ fp32 GEMM
 // C[M,N] = epilogue( sum_k A(m,k) B(k,n) ).  A(m,k) = TA ? A[k*lda+m] : A[m*lda+k];
 // B(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n].  Epilogue: + bias[n], ReLU, multiply by (mask[m*ldc+n] > 0).
-// 64x64x16 tiles, 256 threads, 4x4 micro-tile.  blockIdx.z selects one of up to two independent problems
+// 64x64x32 tiles, 256 threads, 4x4 micro-tile.  blockIdx.z selects one of up to two independent problems
 // (the actor and the critic tower) so both towers share a launch.
 struct GemmProblem {
     const float *A, *B, *bias, *mask;
@@ -515,11 +521,14 @@ struct GemmArgs {
     long long split_stride;
 };
 
+constexpr int GEMM_BK = 32;          // k-extent of a tile: two float4 per thread and operand in flight (see fetch)
+
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
 {
-    __shared__ __align__(16) float As[16][64 + 4];
-    __shared__ __align__(16) float Bs[16][64 + 4];
+    constexpr int BK = GEMM_BK, NH = BK / 16;
+    __shared__ __align__(16) float As[BK][64 + 4];
+    __shared__ __align__(16) float Bs[BK][64 + 4];
     const int ks = g.ksplit > 1 ? g.ksplit : 1;
     const int prob = blockIdx.z / ks, split = blockIdx.z - prob * ks;
     const GemmProblem pr = prob ? g.pr[1] : g.pr[0];
@@ -533,84 +542,69 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    // global -> registers (one float4 of the A tile and one of the B tile per thread), registers -> shared;
-    // the fetch of tile k+1 is issued before the FMAs of tile k so its latency hides behind them
-    auto fetch = [&](int k0, float4 &va, float4 &vb) {
-        va = make_float4(0.f, 0.f, 0.f, 0.f);
-        vb = va;
-        if (!TA) {
-            const int m = tid >> 2, kq = (tid & 3) * 4;            // 64 rows x 4 float4 along k
-            const int gm = m0 + m, gk = k0 + kq;
-            if (gm < g.M) {
-                const float *src = pr.A + (size_t)gm * g.lda + gk;
-                if (gk + 3 < kend) va = *reinterpret_cast<const float4 *>(src);
-                else {
-                    if (gk + 0 < kend) va.x = src[0];
-                    if (gk + 1 < kend) va.y = src[1];
-                    if (gk + 2 < kend) va.z = src[2];
-                }
-            }
-        } else {
-            const int k = tid >> 4, mq = (tid & 15) * 4;           // 16 k x 16 float4 along m
-            const int gk = k0 + k, gm = m0 + mq;
-            if (gk < kend) {
-                const float *src = pr.A + (size_t)gk * g.lda + gm;
-                if (gm + 3 < g.M) va = *reinterpret_cast<const float4 *>(src);
-                else {
-                    if (gm + 0 < g.M) va.x = src[0];
-                    if (gm + 1 < g.M) va.y = src[1];
-                    if (gm + 2 < g.M) va.z = src[2];
-                }
-            }
+    // global -> registers (NH float4 of the A tile and NH of the B tile per thread), registers -> shared; the fetch of
+    // tile k+1 is issued before the FMAs of tile k so its latency hides behind them.  These GEMMs are a few CTAs with
+    // K <= 260 per split: a k-step costs one memory round trip, so the tile is 32 deep to halve the number of steps.
+    auto load4 = [&](const float *src, int i, int lim) {          // src[0..3], elements at index >= lim read as zero
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i + 3 < lim) v = *reinterpret_cast<const float4 *>(src);
+        else {
+            if (i + 0 < lim) v.x = src[0];
+            if (i + 1 < lim) v.y = src[1];
+            if (i + 2 < lim) v.z = src[2];
         }
-        if (TB) {
-            const int n = tid >> 2, kq = (tid & 3) * 4;
-            const int gn = n0 + n, gk = k0 + kq;
-            if (gn < g.N) {
-                const float *src = pr.B + (size_t)gn * g.ldb + gk;
-                if (gk + 3 < kend) vb = *reinterpret_cast<const float4 *>(src);
-                else {
-                    if (gk + 0 < kend) vb.x = src[0];
-                    if (gk + 1 < kend) vb.y = src[1];
-                    if (gk + 2 < kend) vb.z = src[2];
-                }
+        return v;
+    };
+    auto fetch = [&](int k0, float4 (&va)[NH], float4 (&vb)[NH]) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            va[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[h] = va[h];
+            if (!TA) {
+                const int m = tid >> 2, kq = (tid & 3) * 4 + 16 * h;       // 64 rows x 4 float4 along k
+                const int gm = m0 + m, gk = k0 + kq;
+                if (gm < g.M) va[h] = load4(pr.A + (size_t)gm * g.lda + gk, gk, kend);
+            } else {
+                const int k = (tid >> 4) + 16 * h, mq = (tid & 15) * 4;    // 16 k x 16 float4 along m
+                const int gk = k0 + k, gm = m0 + mq;
+                if (gk < kend) va[h] = load4(pr.A + (size_t)gk * g.lda + gm, gm, g.M);
             }
-        } else {
-            const int k = tid >> 4, nq = (tid & 15) * 4;
-            const int gk = k0 + k, gn = n0 + nq;
-            if (gk < kend) {
-                const float *src = pr.B + (size_t)gk * g.ldb + gn;
-                if (gn + 3 < g.N) vb = *reinterpret_cast<const float4 *>(src);
-                else {
-                    if (gn + 0 < g.N) vb.x = src[0];
-                    if (gn + 1 < g.N) vb.y = src[1];
-                    if (gn + 2 < g.N) vb.z = src[2];
-                }
+            if (TB) {
+                const int n = tid >> 2, kq = (tid & 3) * 4 + 16 * h;
+                const int gn = n0 + n, gk = k0 + kq;
+                if (gn < g.N) vb[h] = load4(pr.B + (size_t)gn * g.ldb + gk, gk, kend);
+            } else {
+                const int k = (tid >> 4) + 16 * h, nq = (tid & 15) * 4;
+                const int gk = k0 + k, gn = n0 + nq;
+                if (gk < kend) vb[h] = load4(pr.B + (size_t)gk * g.ldb + gn, gn, g.N);
             }
         }
     };
-    auto stash = [&](const float4 &va, const float4 &vb) {
-        if (!TA) {
-            const int m = tid >> 2, kq = (tid & 3) * 4;
-            As[kq + 0][m] = va.x; As[kq + 1][m] = va.y; As[kq + 2][m] = va.z; As[kq + 3][m] = va.w;
-        } else {
-            *reinterpret_cast<float4 *>(&As[tid >> 4][(tid & 15) * 4]) = va;
-        }
-        if (TB) {
-            const int n = tid >> 2, kq = (tid & 3) * 4;
-            Bs[kq + 0][n] = vb.x; Bs[kq + 1][n] = vb.y; Bs[kq + 2][n] = vb.z; Bs[kq + 3][n] = vb.w;
-        } else {
-            *reinterpret_cast<float4 *>(&Bs[tid >> 4][(tid & 15) * 4]) = vb;
+    auto stash = [&](const float4 (&va)[NH], const float4 (&vb)[NH]) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            if (!TA) {
+                const int m = tid >> 2, kq = (tid & 3) * 4 + 16 * h;
+                As[kq + 0][m] = va[h].x; As[kq + 1][m] = va[h].y; As[kq + 2][m] = va[h].z; As[kq + 3][m] = va[h].w;
+            } else {
+                *reinterpret_cast<float4 *>(&As[(tid >> 4) + 16 * h][(tid & 15) * 4]) = va[h];
+            }
+            if (TB) {
+                const int n = tid >> 2, kq = (tid & 3) * 4 + 16 * h;
+                Bs[kq + 0][n] = vb[h].x; Bs[kq + 1][n] = vb[h].y; Bs[kq + 2][n] = vb[h].z; Bs[kq + 3][n] = vb[h].w;
+            } else {
+                *reinterpret_cast<float4 *>(&Bs[(tid >> 4) + 16 * h][(tid & 15) * 4]) = vb[h];
+            }
         }
     };
-    float4 va, vb;
+    float4 va[NH], vb[NH];
     if (kbeg < kend) fetch(kbeg, va, vb);
-    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
         stash(va, vb);
         __syncthreads();
-        if (k0 + 16 < kend) fetch(k0 + 16, va, vb);
+        if (k0 + BK < kend) fetch(k0 + BK, va, vb);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < BK; ++k) {
             const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
             const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -1010,6 +1004,31 @@ __global__ void gather_scalar_kernel(const float *__restrict__ src, const int64_
     dst[t] = src[idx[r] * row + j];
 }
 
+// The six arrays of one PPO minibatch (observation stack, goal | speed, action, log-prob, advantage, target:
+// model/ppo.py:162-169) gathered by the same index in ONE launch: blockIdx.y = array, blockIdx.x covers the largest.
+struct GatherMulti {
+    const float *src[RLCA_GATHER_MAX];
+    float *dst[RLCA_GATHER_MAX];
+    int row[RLCA_GATHER_MAX];
+};
+
+__global__ void gather_multi_kernel(const GatherMulti g, const int64_t *__restrict__ idx, int nrows)
+{
+    const int a = blockIdx.y;
+    const int row = g.row[a];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((row & 3) == 0) {
+        const int row4 = row >> 2;
+        if (t >= (int64_t)nrows * row4) return;
+        const int r = (int)(t / row4), j = (int)(t - (int64_t)r * row4);
+        reinterpret_cast<float4 *>(g.dst[a])[t] = reinterpret_cast<const float4 *>(g.src[a])[idx[r] * row4 + j];
+    } else {
+        if (t >= (int64_t)nrows * row) return;
+        const int r = (int)(t / row), j = (int)(t - (int64_t)r * row);
+        g.dst[a][t] = g.src[a][idx[r] * row + j];
+    }
+}
+
 // ------------------------------------------------------------------------------------ host API
 extern "C" int rlca_adv_moments(const float *x, int64_t n, double *moments, void *stream)
 {
@@ -1044,6 +1063,28 @@ extern "C" int rlca_gather_rows(const float *src, const int64_t *idx, int32_t ro
     return RLCA_OK;
 }
 
+extern "C" int rlca_gather_minibatch(const float *const *src, const int32_t *row_floats, int32_t narrays,
+                                     const int64_t *idx, int32_t nrows, float *const *dst, void *stream)
+{
+    if (!src || !row_floats || !idx || !dst || narrays < 1 || narrays > RLCA_GATHER_MAX || nrows < 1)
+        return rlca_set_err(RLCA_ERR_INVALID, "bad gather_minibatch arguments");
+    GatherMulti g{};
+    int64_t most = 0;
+    for (int a = 0; a < narrays; ++a) {
+        if (!src[a] || !dst[a] || row_floats[a] < 1) return rlca_set_err(RLCA_ERR_INVALID, "bad gather_minibatch array");
+        // the float4 path needs 16-byte aligned rows on both sides
+        const bool vec = (row_floats[a] & 3) == 0 && (((uintptr_t)src[a] | (uintptr_t)dst[a]) & 15) == 0;
+        g.src[a] = src[a]; g.dst[a] = dst[a];
+        g.row[a] = row_floats[a];
+        if (!vec && (row_floats[a] & 3) == 0) return rlca_set_err(RLCA_ERR_INVALID, "gather_minibatch: rows of 4k floats must be 16-byte aligned");
+        const int64_t units = (int64_t)nrows * (vec ? row_floats[a] / 4 : row_floats[a]);
+        if (units > most) most = units;
+    }
+    gather_multi_kernel<<<dim3((unsigned)((most + 255) / 256), narrays), 256, 0, (cudaStream_t)stream>>>(g, idx, nrows);
+    RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
 extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
 {
     if (!out || max_batch < 1) return rlca_set_err(RLCA_ERR_INVALID, "bad max_batch/out");
@@ -1069,6 +1110,19 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
     RLCA_CUDA_TRY(cudaMalloc(&p->red, 64 * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->Wc, 2 * CONV_WBLK * sizeof(float)));
     RLCA_CUDA_TRY(cudaMalloc(&p->S, (size_t)RSPLIT * 2 * 128 * XLD * sizeof(float)));
+    RLCA_CUDA_TRY(cudaMalloc(&p->S2, (size_t)RSPLIT * 2 * CONV_PART * sizeof(float)));
+    for (int i = 0; i < 2; ++i) {
+        RLCA_CUDA_TRY(cudaStreamCreateWithFlags(&p->side[i], cudaStreamNonBlocking));
+        RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
+    RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_heads, cudaEventDisableTiming));
+    RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_dx, cudaEventDisableTiming));
+    RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_split, cudaEventDisableTiming));
+    {
+        const char *e = getenv("RLCA_BWD_STREAMS");          // read once, at creation
+        p->use_side = !(e && atoi(e) == 0);
+    }
     p->bpad = (max_batch + 31) / 32 * 32;
     {
         const size_t BP = (size_t)p->bpad;
@@ -1106,6 +1160,12 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
     if (!p) return RLCA_OK;
     cudaFree(p->F); cudaFree(p->X); cudaFree(p->H2); cudaFree(p->dOut); cudaFree(p->dZ2); cudaFree(p->dX);
     cudaFree(p->dF); cudaFree(p->part); cudaFree(p->headpart); cudaFree(p->red); cudaFree(p->S); cudaFree(p->Wc);
+    cudaFree(p->S2);
+    for (int i = 0; i < 2; ++i) { if (p->side[i]) cudaStreamDestroy(p->side[i]); if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]); }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_heads) cudaEventDestroy(p->ev_heads);
+    if (p->ev_dx) cudaEventDestroy(p->ev_dx);
+    if (p->ev_split) cudaEventDestroy(p->ev_split);
     cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P); cudaFree(p->Wimg); cudaFree(p->WimgB);
     delete p;
     return RLCA_OK;
@@ -1274,11 +1334,46 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     // padding floats between tensors must stay zero for the optimizer / all-reduce
     RLCA_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)tensor_offset(RLCA_POLICY_NTENSORS), s));
     RLCA_CUDA_TRY(cudaMemcpyAsync(grads + tensor_offset(T_LOGSTD), pol->red, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    // Streams: s carries the chain the conv towers wait for (heads -> dX -> split of dZ1 -> dF); s0 the transposed split
+    // of F (needs only the forward) and the dW_fc1 GEMM; s1 the small weight / bias gradients.  One stream when the
+    // tensor-core path is off, on request, or while a data-parallel caller waits on fc_grads_event.
+    const bool side = pol->use_side && pol->use_tc && !pol->fc_grads_event;
+    cudaStream_t s0 = side ? pol->side[0] : s, s1 = side ? pol->side[1] : s;
+    const size_t WSZ = (size_t)256 * FEAT;
+    const size_t BP = (size_t)((nb + 31) / 32 * 32);
+    RlcaTcProblem pw[2], pf[2];
+    const float *dzsrc[2], *fsrc[2];
+    float *dzh[2], *dzl[2], *dzth[2], *dztl[2], *fth[2], *ftl[2];
+    for (int t = 0; t < 2; ++t) {
+        dzsrc[t] = pol->dX + (size_t)t * B * XLD;                              // dZ1 [nb,256], pitch 260
+        fsrc[t] = pol->F + (size_t)t * B * FEAT;
+        dzh[t] = pol->dZs + (size_t)(2 * t) * B * 256; dzl[t] = dzh[t] + B * 256;
+        dzth[t] = pol->dZTs + (size_t)(2 * t) * 256 * BP; dztl[t] = dzth[t] + 256 * BP;
+        fth[t] = pol->FTs + (size_t)(2 * t) * FEAT * BP; ftl[t] = fth[t] + FEAT * BP;
+        // dW_fc1 (256 x 4096) = dZ1^T F : A = dZ1^T [256, nb], B = F^T [4096, nb]
+        pw[t] = RlcaTcProblem{dzth[t], dztl[t], fth[t], ftl[t], (int)BP, (int)BP, t == 0 ? ga.fc1w : gc.fc1w, nullptr};
+        // dF (nb x 4096) = dZ1 W_fc1 : A = dZ1 [nb,256], B = W1^T [4096,256]; the relu(conv2) mask is applied by the
+        // consumer (conv_tower_bwd) so this output-bound GEMM's epilogue is a pure coalesced store
+        pf[t] = RlcaTcProblem{dzh[t], dzl[t], pol->W1Ts + (size_t)(2 * t) * WSZ, pol->W1Ts + (size_t)(2 * t + 1) * WSZ, 256, 256,
+                              pol->dF + (size_t)t * B * FEAT, nullptr};
+    }
+    if (side) {
+        RLCA_CUDA_TRY(cudaEventRecord(pol->ev_fork, s));         // after the memset of the gradient buffer
+        RLCA_CUDA_TRY(cudaStreamWaitEvent(s0, pol->ev_fork, 0));
+        RLCA_CUDA_TRY(cudaStreamWaitEvent(s1, pol->ev_fork, 0));
+    }
+    if (pol->use_tc && side)
+        for (int t = 0; t < 2; ++t)      // (one launch per tower measured faster than the fused two-tower launch: 88 vs 124 us at 4104)
+            rlca_tc_transpose_split(fsrc[t], nb, FEAT, FEAT, fth[t], ftl[t], (int)BP, s0);
     const int chunks = (nb + HEAD_CHUNK - 1) / HEAD_CHUNK;
     heads_bwd_kernel<<<chunks, 128, 0, s>>>(pol->H2, pol->dOut, params + tensor_offset(T_A1W),
                                             params + tensor_offset(T_A2W), params + tensor_offset(T_CRITW), nb, pol->dZ2,
                                             pol->headpart);
-    heads_part_reduce_kernel<<<3, HPR_GROUPS * 132, 0, s>>>(pol->headpart, chunks, grads + tensor_offset(T_A1W),
+    if (side) {
+        RLCA_CUDA_TRY(cudaEventRecord(pol->ev_heads, s));
+        RLCA_CUDA_TRY(cudaStreamWaitEvent(s1, pol->ev_heads, 0));
+    }
+    heads_part_reduce_kernel<<<3, HPR_GROUPS * 132, 0, s1>>>(pol->headpart, chunks, grads + tensor_offset(T_A1W),
                                                grads + tensor_offset(T_A1B), grads + tensor_offset(T_A2W),
                                                grads + tensor_offset(T_A2B), grads + tensor_offset(T_CRITW),
                                                grads + tensor_offset(T_CRITB));
@@ -1286,52 +1381,45 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     ColsumArgs cs{};
     cs.A[0] = pol->dZ2; cs.A[1] = pol->dZ2 + B * 128; cs.P = pol->S;
     cs.rows = nb; cs.cols = 128; cs.ld = 128;
-    colsum_kernel<<<dim3(4, 2, RSPLIT), 256, 0, s>>>(cs);
-    reduce_splits_kernel<<<dim3(1, 2), 256, 0, s>>>(pol->S, RSPLIT, 128, ga.fc2b, gc.fc2b);
+    colsum_kernel<<<dim3(4, 2, RSPLIT), 256, 0, s1>>>(cs);
+    reduce_splits_kernel<<<dim3(1, 2), 256, 0, s1>>>(pol->S, RSPLIT, 128, ga.fc2b, gc.fc2b);
     GemmArgs g{};
     // dW_fc2 (128 x 260) = dZ2^T X
     g.M = 128; g.N = XLD; g.K = nb; g.lda = 128; g.ldb = XLD; g.ldc = XLD; g.relu = 0;
     g.ksplit = RSPLIT; g.split_stride = 2LL * 128 * XLD;       // partial P[(split*2 + tower)][128][260]
     g.pr[0] = GemmProblem{pol->dZ2, pol->X, nullptr, nullptr, pol->S};
     g.pr[1] = GemmProblem{pol->dZ2 + B * 128, pol->X + B * XLD, nullptr, nullptr, pol->S + 128 * XLD};
-    launch_gemm<true, false>(g, 2, s);
-    reduce_splits_kernel<<<dim3((128 * XLD + 255) / 256, 2), 256, 0, s>>>(pol->S, RSPLIT, 128 * XLD, ga.fc2w, gc.fc2w);
+    launch_gemm<true, false>(g, 2, s1);
+    reduce_splits_kernel<<<dim3((128 * XLD + 255) / 256, 2), 256, 0, s1>>>(pol->S, RSPLIT, 128 * XLD, ga.fc2w, gc.fc2w);
     g.ksplit = 0; g.split_stride = 0;
     // dX (nb x 260) = dZ2 W_fc2, masked by relu(fc1) (columns 256..259 = goal/speed carry no parameter gradient)
     g.M = nb; g.N = 256; g.K = 128; g.lda = 128; g.ldb = XLD; g.ldc = XLD; g.relu = 0;
     g.pr[0] = GemmProblem{pol->dZ2, ta.fc2w, nullptr, pol->X, pol->dX};
     g.pr[1] = GemmProblem{pol->dZ2 + B * 128, tc.fc2w, nullptr, pol->X + B * XLD, pol->dX + B * XLD};
     launch_gemm<false, false>(g, 2, s);
+    if (side) {
+        RLCA_CUDA_TRY(cudaEventRecord(pol->ev_dx, s));
+        RLCA_CUDA_TRY(cudaStreamWaitEvent(s1, pol->ev_dx, 0));
+    }
     // fc1 bias grads
     cs.A[0] = pol->dX; cs.A[1] = pol->dX + B * XLD; cs.P = pol->S;
     cs.rows = nb; cs.cols = 256; cs.ld = XLD;
-    colsum_kernel<<<dim3(8, 2, RSPLIT), 256, 0, s>>>(cs);
-    reduce_splits_kernel<<<dim3(1, 2), 256, 0, s>>>(pol->S, RSPLIT, 256, ga.fc1b, gc.fc1b);
+    colsum_kernel<<<dim3(8, 2, RSPLIT), 256, 0, s1>>>(cs);
+    reduce_splits_kernel<<<dim3(1, 2), 256, 0, s1>>>(pol->S, RSPLIT, 256, ga.fc1b, gc.fc1b);
+    if (side) RLCA_CUDA_TRY(cudaEventRecord(pol->ev_join[1], s1));
     if (pol->use_tc) {
         // both fc1 gradient GEMMs on the tensor cores (operands made K-major by transpose+split kernels)
-        const size_t WSZ = (size_t)256 * FEAT;
-        const size_t BP = (size_t)((nb + 31) / 32 * 32);
-        RlcaTcProblem pw[2], pf[2];
-        const float *dzsrc[2], *fsrc[2];
-        float *dzh[2], *dzl[2], *dzth[2], *dztl[2], *fth[2], *ftl[2];
-        for (int t = 0; t < 2; ++t) {
-            dzsrc[t] = pol->dX + (size_t)t * B * XLD;                              // dZ1 [nb,256], pitch 260
-            fsrc[t] = pol->F + (size_t)t * B * FEAT;
-            dzh[t] = pol->dZs + (size_t)(2 * t) * B * 256; dzl[t] = dzh[t] + B * 256;
-            dzth[t] = pol->dZTs + (size_t)(2 * t) * 256 * BP; dztl[t] = dzth[t] + 256 * BP;
-            fth[t] = pol->FTs + (size_t)(2 * t) * FEAT * BP; ftl[t] = fth[t] + FEAT * BP;
-            // dW_fc1 (256 x 4096) = dZ1^T F : A = dZ1^T [256, nb], B = F^T [4096, nb]
-            pw[t] = RlcaTcProblem{dzth[t], dztl[t], fth[t], ftl[t], (int)BP, (int)BP, t == 0 ? ga.fc1w : gc.fc1w, nullptr};
-            // dF (nb x 4096) = dZ1 W_fc1 : A = dZ1 [nb,256], B = W1^T [4096,256]; the relu(conv2) mask is applied by the
-            // consumer (conv_tower_bwd) so this output-bound GEMM's epilogue is a pure coalesced store
-            pf[t] = RlcaTcProblem{dzh[t], dzl[t], pol->W1Ts + (size_t)(2 * t) * WSZ, pol->W1Ts + (size_t)(2 * t + 1) * WSZ, 256, 256,
-                                  pol->dF + (size_t)t * B * FEAT, nullptr};
-        }
         rlca_tc_split_both(dzsrc, nb, 256, XLD, dzh, dzl, 256, dzth, dztl, (int)BP, s);
-        for (int t = 0; t < 2; ++t)      // (one launch per tower measured faster than the fused two-tower launch: 88 vs 124 us at 4104)
-            rlca_tc_transpose_split(fsrc[t], nb, FEAT, FEAT, fth[t], ftl[t], (int)BP, s);
-        int rc = rlca_tc_gemm(pw, 2, 256, FEAT, nb, FEAT, 1, 0, s);
+        if (side) {
+            RLCA_CUDA_TRY(cudaEventRecord(pol->ev_split, s));
+            RLCA_CUDA_TRY(cudaStreamWaitEvent(s0, pol->ev_split, 0));
+        } else {
+            for (int t = 0; t < 2; ++t)
+                rlca_tc_transpose_split(fsrc[t], nb, FEAT, FEAT, fth[t], ftl[t], (int)BP, s);
+        }
+        int rc = rlca_tc_gemm(pw, 2, 256, FEAT, nb, FEAT, 1, 0, s0);
         if (rc) return rc;
+        if (side) RLCA_CUDA_TRY(cudaEventRecord(pol->ev_join[0], s0));
         // every gradient outside the conv towers (97 % of the buffer) is final here: a data-parallel caller starts their
         // all-reduce now, under the dF GEMM and the conv tower backward that follow
         if (pol->fc_grads_event) RLCA_CUDA_TRY(cudaEventRecord(pol->fc_grads_event, s));
@@ -1364,13 +1452,17 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
         int rc = rlca_conv_tc_backward(obs, pol->WimgB, pol->dF, pol->F, pol->part, nb, bwd_sms, s);
         if (rc) return rc;
         conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(
-            pol->part, rlca_conv_tc_bwd_slots(nb, bwd_sms), pol->S);
+            pol->part, rlca_conv_tc_bwd_slots(nb, bwd_sms), pol->S2);
     } else {
         conv_tower_bwd_kernel<<<dim3((nb + CONV_SPC - 1) / CONV_SPC, 2), 256, sizeof(ConvBwdSmem), s>>>(
             obs, pol->Wc, ta, tc, pol->dF, pol->use_tc ? pol->F : nullptr, pol->part, nb);
-        conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(pol->part, nb, pol->S);
+        conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(pol->part, nb, pol->S2);
     }
-    conv_part_final_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->S, RSPLIT, ga, gc);
+    conv_part_final_kernel<<<dim3((CONV_PART + 255) / 256, 2), 256, 0, s>>>(pol->S2, RSPLIT, ga, gc);
+    if (side) {                          // the caller's stream continues (all-reduce, optimizer) when every gradient is final
+        RLCA_CUDA_TRY(cudaStreamWaitEvent(s, pol->ev_join[0], 0));
+        RLCA_CUDA_TRY(cudaStreamWaitEvent(s, pol->ev_join[1], 0));
+    }
     pol->launches += 10;
     RLCA_CUDA_TRY(cudaGetLastError());
     return RLCA_OK;

@@ -109,8 +109,21 @@ def normalize_advantages(advs, process_group=None):
     return out.view(advs.shape)
 
 
-def _gather(lib, src, idx, row, dst, dev):
-    _lib.check(lib.rlca_gather_rows(_ptr(src), _ptr(idx), row, idx.numel(), _ptr(dst), _stream(dev)))
+class _MinibatchGather:
+    """The arrays of a minibatch gathered by one sampler index in ONE launch (rlca_gather_minibatch); the pointer
+    tables are built once per update."""
+
+    def __init__(self, lib, srcs, dsts, rows, dev):
+        import ctypes as C
+        self.lib, self.n, self.dev = lib, len(srcs), dev
+        self.keep = (srcs, dsts)                                  # the tensors whose addresses the tables hold
+        self.src = (C.c_void_p * self.n)(*[t.data_ptr() for t in srcs])
+        self.dst = (C.c_void_p * self.n)(*[t.data_ptr() for t in dsts])
+        self.rows = (C.c_int32 * self.n)(*rows)
+
+    def __call__(self, index):
+        _lib.check(self.lib.rlca_gather_minibatch(self.src, self.rows, self.n, _ptr(index), index.numel(), self.dst,
+                                                  _stream(self.dev)))
 
 
 def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_entropy, clip_value, num_step, num_env,
@@ -166,6 +179,8 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
     log = torch.zeros(max(1, epoch * nbatches), 3, device=dev)
     ws = policy._workspace(bs)
     st = _stream(dev)
+    gather = _MinibatchGather(lib, (obss, gs, actions, logprobs, advs, targets), (b_obs, b_gs, b_act, b_lp, b_adv, b_tgt),
+                              (frames * obs_size, 4, act_size, 1, 1, 1), dev)
     k = 0
     for update in range(epoch):
         if permutations is not None:
@@ -176,12 +191,7 @@ def _ppo_update(policy: CNNPolicy, optimizer, batch_size, memory, epoch, coeff_e
             nb = sizes[bi]
             if nb > 0:
                 index = perm[bi * bs:bi * bs + nb].contiguous()
-                _gather(lib, obss, index, frames * obs_size, b_obs, dev)
-                _gather(lib, gs, index, 4, b_gs, dev)
-                _gather(lib, actions, index, act_size, b_act, dev)
-                _gather(lib, logprobs, index, 1, b_lp, dev)
-                _gather(lib, advs, index, 1, b_adv, dev)
-                _gather(lib, targets, index, 1, b_tgt, dev)
+                gather(index)
                 _lib.check(lib.rlca_policy_forward(ws, _ptr(policy.flat), _ptr(b_obs), _ptr(b_gs), nb, _ptr(v), _ptr(mean), st))
                 _lib.check(lib.rlca_ppo_loss_fwd_bwd_weighted(ws, _ptr(policy.flat), _ptr(v), _ptr(mean), _ptr(b_act),
                                                               _ptr(b_lp), _ptr(b_adv), _ptr(b_tgt), nb, clip_value,

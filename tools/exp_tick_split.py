@@ -29,7 +29,10 @@ def graph_time(fn, n=100, reps=10):
 
 
 if __name__ == '__main__':
+    only = sys.argv[1:]                                   # optional: scenario names to run
     for scen, worlds, ar in (('stage1', 171, 1), ('stage2', 94, 2), ('circle', 41, 1)):
+        if only and scen not in only:
+            continue
         env = StageWorld(512, scenario=scen, num_worlds=worlds, seed=0, auto_reset=ar)
         env.reset_pose()
         acts = [torch.rand(env.N, 2, device='cuda') for _ in range(16)]
