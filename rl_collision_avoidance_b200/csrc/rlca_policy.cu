@@ -507,7 +507,7 @@ __global__ void conv_part_final_kernel(const float *__restrict__ P, int splits, 
 // ------------------------------------------------------------------------------------ fp32 GEMM
 // C[M,N] = epilogue( sum_k A(m,k) B(k,n) ).  A(m,k) = TA ? A[k*lda+m] : A[m*lda+k];
 // B(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n].  Epilogue: + bias[n], ReLU, multiply by (mask[m*ldc+n] > 0).
-// 64x64x32 tiles, 256 threads, 4x4 micro-tile.  blockIdx.z selects one of up to two independent problems
+// 64x64x32 (or 32x64x32) tiles, 256 threads, 4x4 (2x4) micro-tile.  blockIdx.z selects one of up to two independent problems
 // (the actor and the critic tower) so both towers share a launch.
 struct GemmProblem {
     const float *A, *B, *bias, *mask;
@@ -521,30 +521,31 @@ struct GemmArgs {
     long long split_stride;
 };
 
-constexpr int GEMM_BK = 32;          // k-extent of a tile: two float4 per thread and operand in flight (see fetch)
+constexpr int GEMM_BK = 32;          // k-extent of a tile
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, int BM>
 __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
 {
-    constexpr int BK = GEMM_BK, NH = BK / 16;
-    __shared__ __align__(16) float As[BK][64 + 4];
-    __shared__ __align__(16) float Bs[BK][64 + 4];
+    constexpr int BK = GEMM_BK, BN = 64, RM = BM / 16;             // RM x 4 micro-tile per thread
+    constexpr int NA = BM * BK / 4 / 256, NB = BN * BK / 4 / 256;  // float4 of the A / B tile per thread
+    static_assert(BM == 32 || BM == 64, "tile heights");
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
     const int ks = g.ksplit > 1 ? g.ksplit : 1;
     const int prob = blockIdx.z / ks, split = blockIdx.z - prob * ks;
     const GemmProblem pr = prob ? g.pr[1] : g.pr[0];
     const int kper = ((g.K + ks - 1) / ks + 15) / 16 * 16;
     const int kbeg = split * kper, kend = min(g.K, kbeg + kper);
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int tx = tid & 15, ty = tid >> 4;
-    float acc[4][4];
+    float acc[RM][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-    // global -> registers (NH float4 of the A tile and NH of the B tile per thread), registers -> shared; the fetch of
-    // tile k+1 is issued before the FMAs of tile k so its latency hides behind them.  These GEMMs are a few CTAs with
-    // K <= 260 per split: a k-step costs one memory round trip, so the tile is 32 deep to halve the number of steps.
+    // global -> registers (NA float4 of the A tile and NB of the B tile per thread), registers -> shared; the fetch of
+    // tile k+1 is issued before the FMAs of tile k so its latency hides behind them.
     auto load4 = [&](const float *src, int i, int lim) {          // src[0..3], elements at index >= lim read as zero
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i + 3 < lim) v = *reinterpret_cast<const float4 *>(src);
@@ -555,49 +556,49 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
         }
         return v;
     };
-    auto fetch = [&](int k0, float4 (&va)[NH], float4 (&vb)[NH]) {
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-            va[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-            vb[h] = va[h];
-            if (!TA) {
-                const int m = tid >> 2, kq = (tid & 3) * 4 + 16 * h;       // 64 rows x 4 float4 along k
-                const int gm = m0 + m, gk = k0 + kq;
-                if (gm < g.M) va[h] = load4(pr.A + (size_t)gm * g.lda + gk, gk, kend);
-            } else {
-                const int k = (tid >> 4) + 16 * h, mq = (tid & 15) * 4;    // 16 k x 16 float4 along m
-                const int gk = k0 + k, gm = m0 + mq;
-                if (gk < kend) va[h] = load4(pr.A + (size_t)gk * g.lda + gm, gm, g.M);
-            }
-            if (TB) {
-                const int n = tid >> 2, kq = (tid & 3) * 4 + 16 * h;
-                const int gn = n0 + n, gk = k0 + kq;
-                if (gn < g.N) vb[h] = load4(pr.B + (size_t)gn * g.ldb + gk, gk, kend);
-            } else {
-                const int k = (tid >> 4) + 16 * h, nq = (tid & 15) * 4;
-                const int gk = k0 + k, gn = n0 + nq;
-                if (gk < kend) vb[h] = load4(pr.B + (size_t)gk * g.ldb + gn, gn, g.N);
-            }
+    // element (row, k) of a [rows x BK] tile, float4 along k (operand stored row-major along k) or along the rows
+    auto fetch_op = [&](bool trans, const float *base, int ld, int r0, int rlim, int rows, int k0, int idx) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!trans) {
+            const int r = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
+            const int gr = r0 + r, gk = k0 + kq;
+            if (gr < rlim) v = load4(base + (size_t)gr * ld + gk, gk, kend);
+        } else {
+            const int k = idx / (rows / 4), rq = (idx % (rows / 4)) * 4;
+            const int gk = k0 + k, gr = r0 + rq;
+            if (gk < kend) v = load4(base + (size_t)gk * ld + gr, gr, rlim);
         }
+        return v;
     };
-    auto stash = [&](const float4 (&va)[NH], const float4 (&vb)[NH]) {
+    auto fetch = [&](int k0, float4 (&va)[NA], float4 (&vb)[NB]) {
 #pragma unroll
-        for (int h = 0; h < NH; ++h) {
+        for (int h = 0; h < NA; ++h) va[h] = fetch_op(TA, pr.A, g.lda, m0, g.M, BM, k0, tid + 256 * h);
+#pragma unroll
+        for (int h = 0; h < NB; ++h) vb[h] = fetch_op(!TB, pr.B, g.ldb, n0, g.N, BN, k0, tid + 256 * h);
+    };
+    auto stash = [&](const float4 (&va)[NA], const float4 (&vb)[NB]) {
+#pragma unroll
+        for (int h = 0; h < NA; ++h) {
+            const int idx = tid + 256 * h;
             if (!TA) {
-                const int m = tid >> 2, kq = (tid & 3) * 4 + 16 * h;
+                const int m = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
                 As[kq + 0][m] = va[h].x; As[kq + 1][m] = va[h].y; As[kq + 2][m] = va[h].z; As[kq + 3][m] = va[h].w;
             } else {
-                *reinterpret_cast<float4 *>(&As[(tid >> 4) + 16 * h][(tid & 15) * 4]) = va[h];
+                *reinterpret_cast<float4 *>(&As[idx / (BM / 4)][(idx % (BM / 4)) * 4]) = va[h];
             }
+        }
+#pragma unroll
+        for (int h = 0; h < NB; ++h) {
+            const int idx = tid + 256 * h;
             if (TB) {
-                const int n = tid >> 2, kq = (tid & 3) * 4 + 16 * h;
+                const int n = idx / (BK / 4), kq = (idx % (BK / 4)) * 4;
                 Bs[kq + 0][n] = vb[h].x; Bs[kq + 1][n] = vb[h].y; Bs[kq + 2][n] = vb[h].z; Bs[kq + 3][n] = vb[h].w;
             } else {
-                *reinterpret_cast<float4 *>(&Bs[(tid >> 4) + 16 * h][(tid & 15) * 4]) = vb[h];
+                *reinterpret_cast<float4 *>(&Bs[idx / (BN / 4)][(idx % (BN / 4)) * 4]) = vb[h];
             }
         }
     };
-    float4 va[NH], vb[NH];
+    float4 va[NA], vb[NB];
     if (kbeg < kend) fetch(kbeg, va, vb);
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
         stash(va, vb);
@@ -605,19 +606,21 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
         if (k0 + BK < kend) fetch(k0 + BK, va, vb);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            float av[RM];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < RM; ++i) av[i] = As[k][ty * RM + i];
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < RM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < RM; ++i) {
+        const int gm = m0 + ty * RM + i;
         if (gm >= g.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -633,11 +636,19 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g)
     }
 }
 
+// 64-row tiles unless they would leave most SMs without a CTA (the fc2 products at 1024 rows are 64-128 CTAs of 64 rows)
 template <bool TA, bool TB>
 static void launch_gemm(const GemmArgs &g, int nprob, cudaStream_t s)
 {
-    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, nprob * (g.ksplit > 1 ? g.ksplit : 1));
-    gemm_kernel<TA, TB><<<grid, 256, 0, s>>>(g);
+    const int z = nprob * (g.ksplit > 1 ? g.ksplit : 1);
+    const int nx = (g.N + 63) / 64;
+    if ((long)nx * ((g.M + 63) / 64) * z < 200) {
+        dim3 grid(nx, (g.M + 31) / 32, z);
+        gemm_kernel<TA, TB, 32><<<grid, 256, 0, s>>>(g);
+    } else {
+        dim3 grid(nx, (g.M + 63) / 64, z);
+        gemm_kernel<TA, TB, 64><<<grid, 256, 0, s>>>(g);
+    }
 }
 
 // out_t[j] = sum_s P[(s * 2 + t) * n + j]  (deterministic second stage of every split reduction); grid (ceil(n/256), 2)

@@ -1,37 +1,25 @@
-"""Summarise an .ncu-rep (read here, no GPU needed): key raw metrics + hottest SASS regions."""
+"""Text summary of an .ncu-rep (one block per kernel launch, the metrics the profiles/ summaries quote):
+python tools/ncu_summary.py gpurun_out/x.ncu-rep "header line" > profiles/x_ncu_summary.txt"""
 import csv
 import subprocess
 import sys
 
+METRICS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_thread', 'dram__bytes_read.sum',
+           'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+           'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+           'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+           'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+           'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+           'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 rep = sys.argv[1]
-top = float(sys.argv[2]) if len(sys.argv) > 2 else 0.006
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-hdr = rows[0]
-want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'launch__grid_size',
-        'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
-        'launch__occupancy_limit_warps', 'launch__waves_per_multiprocessor', 'sm__warps_active.avg.pct_of_peak_sustained_active',
-        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__thread_inst_executed_per_inst_executed.ratio',
-        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'lts__t_bytes.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
-        'launch__shared_mem_per_block_dynamic', 'smsp__average_warp_latency_issue_stalled', 'sm__cycles_elapsed.max']
-for i, h in enumerate(hdr):
-    if h in want:
-        print(f'{h:70s}', [r[i] for r in rows[2:5]], rows[1][i])
-src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
-rows = list(csv.reader(src.splitlines()))
-sec = []
+print('# ' + (sys.argv[2] if len(sys.argv) > 2 else rep))
+out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv', '--metrics', ','.join(METRICS)], capture_output=True,
+                     text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
 for r in rows[2:]:
-    if r and r[0] == 'Kernel Name':
-        break
-    if len(r) > 6:
-        sec.append(r)
-h = rows[1]
-ie, ss = h.index('Instructions Executed'), h.index('Warp Stall Sampling (All Samples)')
-tot = sum(int(r[ie] or 0) for r in sec)
-tots = sum(int(r[ss] or 0) for r in sec)
-print('total warp-instructions', tot, 'stall samples', tots)
-for i, r in enumerate(sec):
-    c = int(r[ie] or 0)
-    if c > tot * top or int(r[ss] or 0) > tots * top * 2:
-        print(f'{i:5d} {r[1][:64]:64s} inst {c:9d} {100*c/tot:5.1f}%  stall {100*int(r[ss] or 0)/max(tots,1):5.1f}%')
+    print('== ' + r[hdr.index('Kernel Name')])
+    for m in METRICS:
+        if m in hdr:
+            i = hdr.index(m)
+            print('   %-98s %16s %s' % (m, r[i], units[i]))
