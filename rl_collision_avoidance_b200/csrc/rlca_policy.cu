@@ -109,13 +109,14 @@ struct rlca_policy {
     float *Wimg;     // pre-swizzled tf32 hi/lo image of the conv weights for the tensor-core conv tower
     float *WimgB;    // same for the backward kernel (per tower: conv1 weights | conv2 weights regrouped by tap)
     int conv_bwd_dirty;
+    int wc_dirty;        // Wc (the CUDA-core conv kernels' weight block) is rebuilt only when one of them is about to run
     cudaEvent_t fc_grads_event;   // optional: recorded by rlca_policy_backward once every gradient outside the conv towers is final
     int reserved_sms;             // SMs the persistent conv tower backward leaves free while that event is set (for the collective)
     // ---- side streams of the backward: the work that is not on the chain heads -> dX -> dF -> conv towers (transposed
     // split of F, every weight / bias gradient of the fc layers and the heads) runs beside it
     int use_side;                 // 0: one stream (RLCA_BWD_STREAMS=0, or while fc_grads_event is set)
     cudaStream_t side[2];
-    cudaEvent_t ev_fork, ev_heads, ev_dx, ev_split, ev_join[2];
+    cudaEvent_t ev_fork, ev_heads, ev_dx, ev_split, ev_prep, ev_join[2];
     float *S2;                    // split-reduction scratch of the conv tower partials (the side streams use S meanwhile)
     int64_t launches;
 };
@@ -1130,6 +1131,7 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
     RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_heads, cudaEventDisableTiming));
     RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_dx, cudaEventDisableTiming));
     RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_split, cudaEventDisableTiming));
+    RLCA_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_prep, cudaEventDisableTiming));
     {
         const char *e = getenv("RLCA_BWD_STREAMS");          // read once, at creation
         p->use_side = !(e && atoi(e) == 0);
@@ -1148,6 +1150,7 @@ extern "C" int rlca_policy_create(int32_t max_batch, rlca_policy **out)
         if (rc) return rc;
         p->use_tc = 1;
         p->weights_dirty = 1;
+        p->wc_dirty = 1;
         rc = rlca_conv_tc_init();
         if (rc) return rc;
         RLCA_CUDA_TRY(cudaMalloc(&p->Wimg, rlca_conv_tc_image_floats() * sizeof(float)));
@@ -1177,6 +1180,7 @@ extern "C" int rlca_policy_destroy(rlca_policy *p)
     if (p->ev_heads) cudaEventDestroy(p->ev_heads);
     if (p->ev_dx) cudaEventDestroy(p->ev_dx);
     if (p->ev_split) cudaEventDestroy(p->ev_split);
+    if (p->ev_prep) cudaEventDestroy(p->ev_prep);
     cudaFree(p->Fs); cudaFree(p->W1s); cudaFree(p->W1Ts); cudaFree(p->dZs); cudaFree(p->dZTs); cudaFree(p->FTs); cudaFree(p->P); cudaFree(p->Wimg); cudaFree(p->WimgB);
     delete p;
     return RLCA_OK;
@@ -1201,6 +1205,7 @@ extern "C" int rlca_policy_weights_changed(rlca_policy *p)
     if (!p) return rlca_set_err(RLCA_ERR_INVALID, "policy is NULL");
     p->weights_dirty = 1;
     p->conv_bwd_dirty = 1;
+    p->wc_dirty = 1;
     return RLCA_OK;
 }
 
@@ -1211,6 +1216,7 @@ extern "C" int rlca_policy_set_tensor_cores(rlca_policy *p, int32_t enable)
     p->use_tc_conv = enable == 1 ? 1 : 0;      // 2 = fc1 GEMMs only (conv tower on the CUDA cores)
     p->weights_dirty = 1;
     p->conv_bwd_dirty = 1;
+    p->wc_dirty = 1;
     return RLCA_OK;
 }
 
@@ -1231,7 +1237,6 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
     if (nb < 1 || nb > pol->max_batch) return rlca_set_err(RLCA_ERR_INVALID, "nb exceeds the workspace max_batch");
     cudaStream_t s = (cudaStream_t)stream;
     const TowerPtrs ta = tower_ptrs(params, 0), tc = tower_ptrs(params, 1);
-    if (pol->weights_dirty) conv_prep_weights_kernel<<<dim3((CONV_WBLK + 255) / 256, 2), 256, 0, s>>>(ta, tc, pol->Wc);
     // the tensor-core conv tower stages the scan with 16-byte bulk copies; oddly aligned inputs take the CUDA-core kernel
     if (pol->use_tc && pol->use_tc_conv && ((uintptr_t)obs & 15) == 0) {
         if (pol->weights_dirty) {
@@ -1243,6 +1248,11 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
         int rc = rlca_conv_tc_forward(obs, pol->Wimg, pol->F, pol->Fs, nb, pol->num_sms, s);
         if (rc) return rc;
     } else {
+        if (pol->wc_dirty) {
+            conv_prep_weights_kernel<<<dim3((CONV_WBLK + 255) / 256, 2), 256, 0, s>>>(ta, tc, pol->Wc);
+            pol->wc_dirty = 0;
+            pol->launches += 1;
+        }
         conv_tower_fwd_kernel<<<(nb + CONV_SPC - 1) / CONV_SPC, 256, sizeof(ConvSmem), s>>>(
             obs, pol->Wc, pol->F, pol->use_tc ? pol->Fs : nullptr, nb);
     }
@@ -1291,7 +1301,7 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
     heads_fwd_kernel<<<(nb * 32 + 255) / 256, 256, 0, s>>>(
         pol->H2, params + tensor_offset(T_A1W), params + tensor_offset(T_A1B), params + tensor_offset(T_A2W),
         params + tensor_offset(T_A2B), params + tensor_offset(T_CRITW), params + tensor_offset(T_CRITB), nb, value, mean);
-    pol->launches += 5;
+    pol->launches += 4;
     pol->weights_dirty = 0;
     RLCA_CUDA_TRY(cudaGetLastError());
     return RLCA_OK;
@@ -1373,6 +1383,14 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
         RLCA_CUDA_TRY(cudaStreamWaitEvent(s0, pol->ev_fork, 0));
         RLCA_CUDA_TRY(cudaStreamWaitEvent(s1, pol->ev_fork, 0));
     }
+    const bool tc_conv = pol->use_tc && pol->use_tc_conv && ((uintptr_t)obs & 15) == 0;
+    if (tc_conv && pol->conv_bwd_dirty) {      // weight image of the conv tower backward: needs only the weights (side 1)
+        const float *w1[2] = {ta.cv1w, tc.cv1w}, *b1[2] = {ta.cv1b, tc.cv1b};
+        const float *w2[2] = {ta.cv2w, tc.cv2w}, *b2[2] = {ta.cv2b, tc.cv2b};
+        rlca_conv_tc_bwd_prep(w1, b1, w2, b2, pol->WimgB, s1);
+        if (side) RLCA_CUDA_TRY(cudaEventRecord(pol->ev_prep, s1));
+        pol->launches += 1;
+    }
     if (pol->use_tc && side)
         for (int t = 0; t < 2; ++t)      // (one launch per tower measured faster than the fused two-tower launch: 88 vs 124 us at 4104)
             rlca_tc_transpose_split(fsrc[t], nb, FEAT, FEAT, fth[t], ftl[t], (int)BP, s0);
@@ -1450,14 +1468,11 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
     g.pr[1] = GemmProblem{pol->dX + B * XLD, tc.fc1w, nullptr, pol->F + B * FEAT, pol->dF + B * FEAT};
     launch_gemm<false, false>(g, 2, s);
     }
-    if (pol->use_tc && pol->use_tc_conv && ((uintptr_t)obs & 15) == 0) {
+    if (tc_conv) {
         // conv tower backward on the tensor cores: one partial per CTA instead of one per sample
         if (pol->conv_bwd_dirty) {
-            const float *w1[2] = {ta.cv1w, tc.cv1w}, *b1[2] = {ta.cv1b, tc.cv1b};
-            const float *w2[2] = {ta.cv2w, tc.cv2w}, *b2[2] = {ta.cv2b, tc.cv2b};
-            rlca_conv_tc_bwd_prep(w1, b1, w2, b2, pol->WimgB, s);
+            if (side) RLCA_CUDA_TRY(cudaStreamWaitEvent(s, pol->ev_prep, 0));
             pol->conv_bwd_dirty = 0;
-            pol->launches += 1;
         }
         const int bwd_sms = pol->num_sms - pol->reserved_sms > 8 ? pol->num_sms - pol->reserved_sms : pol->num_sms;
         int rc = rlca_conv_tc_backward(obs, pol->WimgB, pol->dF, pol->F, pol->part, nb, bwd_sms, s);
@@ -1465,6 +1480,11 @@ extern "C" int rlca_policy_backward(rlca_policy *pol, const float *params, const
         conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(
             pol->part, rlca_conv_tc_bwd_slots(nb, bwd_sms), pol->S2);
     } else {
+        if (pol->wc_dirty) {      // (a forward on the tensor-core path followed by a backward that cannot use it)
+            conv_prep_weights_kernel<<<dim3((CONV_WBLK + 255) / 256, 2), 256, 0, s>>>(ta, tc, pol->Wc);
+            pol->wc_dirty = 0;
+            pol->launches += 1;
+        }
         conv_tower_bwd_kernel<<<dim3((nb + CONV_SPC - 1) / CONV_SPC, 2), 256, sizeof(ConvBwdSmem), s>>>(
             obs, pol->Wc, ta, tc, pol->dF, pol->use_tc ? pol->F : nullptr, pol->part, nb);
         conv_part_reduce_kernel<<<dim3((CONV_PART + 255) / 256, 2, RSPLIT), 256, 0, s>>>(pol->part, nb, pol->S2);
