@@ -3,6 +3,8 @@
 The numerics contract makes poses, ranges, rewards and flags exactly
 reproducible, so every comparison here is np.array_equal on the raw bits — tighter than
 the north-star's 1e-4 fp32 tolerance (collision flags bit-exact)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -262,9 +264,10 @@ def test_fused_scan_fifo(built):
 
 
 def test_circle_world_global_grid_path(built):
-    """circle.world (60 x 60 m at 0.01 m = 6000 x 6000 cells, 50 robots, antipodal goals) does not fit shared memory:
-    the library keeps one owner grid per world in global memory and runs the tick as physics+mark / lidar / unmark
-    launches.  Same oracle, same bit-exact bar (reset, observe, ticks incl. the |w| > 0.7 penalty, raycast)."""
+    """circle.world (60 x 60 m at 0.01 m = 6000 x 6000 cells, 50 robots, antipodal goals): no first-hit table at this
+    size - the library walks the static map through a distance field and scatters the other robots' outlines through
+    the inverse walk lists (rlca_big_lidar_kernel).  Same oracle, same bit-exact bar (reset, observe, ticks incl. the
+    |w| > 0.7 penalty, raycast)."""
     sc, env, orc = make_pair('circle', num_worlds=2, auto_reset=1, seed=3)
     orc.reset_world()
     assert_state_equal(env, orc, 'reset_world')
@@ -289,6 +292,49 @@ def test_circle_world_global_grid_path(built):
     got = env.raycast(torch.from_numpy(pose).cuda()).cpu().numpy()
     ref = orc.raycast(pose)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_circle_raycast_walls_corners_outside(built):
+    """The big-map lidar's static part on hand-placed poses: robots 5 cm to 6.5 m from a wall of circle.world at all
+    headings (distance-field walks of 1 to many jumps; the start-cell distance comes from shared memory), in the four
+    corners, ON the wall cells, outside the floor plan (no distance field there: the walk reads the template), and
+    pairs close enough for the long inverse lists of the scatter.  Scans must equal the cell-marching oracle's."""
+    sc, env, orc = make_pair('circle', num_worlds=2, auto_reset=1, seed=5)
+    orc.reset_world()
+    env.reset_pose()
+    orc.reset_pose()
+    rng = np.random.default_rng(12)
+    N = orc.N
+    pose = orc.pose.copy()
+    k = 0
+    for d in (0.05, 0.11, 0.3, 0.8, 1.7, 3.0, 4.4, 5.9, 6.05, 6.5):          # distance to the wall at x = +30 / y = -30
+        pose[k, :3] = (30.0 - d, rng.uniform(-20, 20), rng.uniform(-np.pi, np.pi)); k += 1
+        pose[k, :3] = (rng.uniform(-20, 20), -30.0 + d, rng.uniform(-np.pi, np.pi)); k += 1
+    for sx in (-1, 1):
+        for sy in (-1, 1):                                                   # corners, 0.4 m and 3 m inside
+            pose[k, :3] = (sx * 29.6, sy * 29.6, rng.uniform(-np.pi, np.pi)); k += 1
+            pose[k, :3] = (sx * 27.0, sy * 27.0, math.atan2(sy, sx)); k += 1
+    for x, y in ((30.0, 0.0), (-30.005, 3.0), (31.0, 0.0), (-36.5, -2.0), (0.0, 33.0), (29.0, 40.0)):   # on / beyond the walls
+        pose[k, :3] = (x, y, rng.uniform(-np.pi, np.pi)); k += 1
+    for i in range(6):                                                       # tight cluster: cells next to the viewer
+        pose[k, :3] = (10.0 + 0.45 * (i % 3), -4.0 + 0.5 * (i // 3), rng.uniform(-np.pi, np.pi)); k += 1
+    assert k <= 50
+    pose[50:, :3] = pose[:50, :3]                                            # second world: same places, other headings
+    pose[50:, 2] = rng.uniform(-np.pi, np.pi, 50)
+    pose = pose.astype(np.float32)
+    got = env.raycast(torch.from_numpy(pose).cuda()).cpu().numpy()
+    ref = orc.raycast(pose)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), np.argwhere(got != ref)[:5]
+    assert (ref < 5.99).mean() > 0.2 and (ref > 5.99).any()                  # walls and robots seen, and free beams too
+    # the tick from those poses (collision against walls for the robots on / at them, re-spawns)
+    env.control_pose(torch.from_numpy(pose[:, :3].copy()))
+    orc.pose[:] = env.state['pose'].cpu().numpy()
+    orc.observe()
+    assert_outputs_equal(env, orc, 'scan after control_pose')
+    a = random_actions(rng, N)
+    env.control_vel(torch.from_numpy(a).cuda())
+    orc.step(a)
+    assert_outputs_equal(env, orc, 'tick from the hand-placed poses')
 
 
 @pytest.mark.parametrize('scenario', ['stage1', 'stage2'])

@@ -129,3 +129,4 @@ def test_beams_with_the_same_truncated_end_point_share_the_walk():
     keys = [(int(R * math.cos(-fov / 2 + i * fov / 511)), int(R * math.sin(-fov / 2 + i * fov / 511))) for i in range(512)]
     distinct = 1 + sum(keys[i] != keys[i - 1] for i in range(1, 512))
     assert 80 <= distinct <= 130
+
