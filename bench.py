@@ -435,6 +435,46 @@ def section_train(torch, dev):
             'rollout_agent_steps_per_s': 128 * N / roll}
 
 
+def section_circle_dp(torch, dist, dev, rank, world_size, n=100):
+    """BASELINE config 4 at N > 1: circle.world, 41 worlds x 50 robots per GPU (16 400 robots at N = 8), worlds sharded
+    over the ranks (no data-path collective); graph-replayed ticks, max over ranks.  Its policy-gradient all-reduce is
+    the learner_dp section."""
+    import numpy as np
+    from rl_collision_avoidance_b200.stage_world import StageWorld
+    worlds = 41
+    env = StageWorld(BEAMS, scenario='circle', num_worlds=worlds, device=dev, seed=0, auto_reset=1,
+                     world_offset=rank * worlds)
+    env.reset_pose()
+    rng = np.random.default_rng(7 + rank)
+    acts = [torch.from_numpy(random_actions(rng, env.N)).to(dev) for _ in range(16)]
+    slots = max(2, int(300e6 / (env.N * BEAMS * 4)) + 1)
+    ring = torch.empty(slots, env.N, BEAMS, device=dev)
+
+    def tick(i):
+        env.control_vel(acts[i % 16], obs_out=ring[i % slots])
+    for i in range(10):
+        tick(i)
+    torch.cuda.synchronize(dev)
+    G = 2 * max(1, min(n, 2 * slots) // 2)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(G):
+            tick(i)
+    graph.replay()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    ms = gpu_time(torch, dev, lambda i: graph.replay(), max(1, n // G), warm=1) / G
+    t = torch.tensor([ms], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    N = env.N
+    env.close()
+    del env, ring
+    us = float(t.item()) * 1e3
+    return {'workload': f'circle: {world_size} GPUs x {worlds} worlds x 50 robots = {N * world_size} agents, {BEAMS} beams, '
+                        'auto_reset=1, worlds sharded over the ranks', 'us_per_tick': us,
+            'agent_steps_per_s': N * world_size / (us * 1e-6), 'scaling': 'weak'}
+
+
 def section_learner_dp(torch, dist, dev, world_size):
     """Data-parallel minibatch step (N > 1): forward + loss + backward + NCCL all-reduce of the flat gradient + Adam
     with the 1/world folded in, at batch 1024 per rank (model/ppo.py:172-188 per optimizer step)."""
@@ -677,12 +717,16 @@ def main():
     if args.e2e_sweep:
         e2e_sweep = {f'mode{m}_chunks{k}': time_e2e(chunks=k, mode=m) for m in (0, 2) for k in (1, 2, 3, 4, 8)}
 
-    learner_dp = None
+    learner_dp, circle_dp = None, None
     if world_size > 1 and not args.no_sections:
         try:
             learner_dp = section_learner_dp(torch, dist, dev, world_size)
         except Exception as e:                           # an extra section must not lose the headline line
             learner_dp = {'error': repr(e)}
+        try:
+            circle_dp = section_circle_dp(torch, dist, dev, rank, world_size)
+        except Exception as e:
+            circle_dp = {'error': repr(e)}
 
     if rank == 0:
         value = N * world_size * args.steps / (ms_max * 1e-3)
@@ -729,6 +773,8 @@ def main():
             line['e2e_sweep_host_chunks'] = e2e_sweep
         if learner_dp is not None:
             line['learner_dp'] = learner_dp
+        if circle_dp is not None:
+            line['circle_config4'] = circle_dp
         cores = None
         if world_size == 1 and not args.no_cpu:
             val, cores, sample, _ = run_cpu(args.cpu_steps, 3, budget_s=25.0)
