@@ -496,9 +496,9 @@ def section_learner_dp(torch, dist, dev, world_size):
         _lib.check(lib.rlca_policy_backward(ws, _ptr(pol.flat), _ptr(obs), _ptr(gs), nb, _ptr(pol.grad), st))
 
     from rl_collision_avoidance_b200.parallel import OverlappedGradSync
-    sync = OverlappedGradSync(pol)
+    sync = None
 
-    def full(_=0):                   # what model/ppo.py runs: fc-side ranges all-reduced under the rest of the backward
+    def full(_=0):                   # RLCA_DP_OVERLAP=1: fc-side ranges all-reduced under the rest of the backward
         compute()
         sync.reduce()
         opt.step(grad_scale=1.0 / world_size)
@@ -516,9 +516,13 @@ def section_learner_dp(torch, dist, dev, world_size):
         dist.all_reduce(pol.grad)
 
     res = {}
-    variants = [('step_overlapped_allreduce_us', full), ('step_serial_allreduce_us', serial),
-                ('step_without_allreduce_us', local), ('allreduce_alone_us', ar)]
+    # the overlapped variant last: while its gradient event is set the backward runs on one stream and leaves 16 SMs to
+    # the collective, which must not leak into the other variants
+    variants = [('step_serial_allreduce_us', serial), ('step_without_allreduce_us', local), ('allreduce_alone_us', ar),
+                ('step_overlapped_allreduce_us', full)]
     for k, fn in variants:
+        if fn is full:
+            sync = OverlappedGradSync(pol)
         ms = gpu_time(torch, dev, fn, 20, warm=5)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
