@@ -303,7 +303,13 @@ int rlca_ppo_loss_fwd_bwd_weighted(rlca_policy *pol, const float *params_dev, co
                                    void *stream);
 
 /* Backward of the whole network for the batch of the last rlca_policy_forward: writes the
- * flat gradient buffer (RLCA_POLICY_NPARAMS floats; overwritten, not accumulated). */
+ * flat gradient buffer (RLCA_POLICY_NPARAMS floats; overwritten, not accumulated).
+ * Stream semantics: the call orders all of its work after what is already enqueued on `stream`, and everything the
+ * caller enqueues on `stream` afterwards (all-reduce, optimizer, the next forward) after all of its work - as if it had
+ * run on `stream` alone.  Internally the weight / bias gradients and the operand transposes that are not on the chain
+ * heads -> dX -> dF -> conv towers run on two streams owned by the workspace (forked and joined with events; no host
+ * synchronisation).  RLCA_BWD_STREAMS=0 in the environment when the workspace is created keeps one stream;
+ * so does a gradient event (rlca_policy_set_grad_event). */
 int rlca_policy_backward(rlca_policy *pol, const float *params_dev, const float *obs_dev, const float *gs_dev,
                          int32_t nb, float *grads_dev, void *stream);
 
