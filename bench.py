@@ -442,27 +442,34 @@ def section_circle_dp(torch, dist, dev, rank, world_size, n=100):
     import numpy as np
     from rl_collision_avoidance_b200.stage_world import StageWorld
     worlds = 41
-    env = StageWorld(BEAMS, scenario='circle', num_worlds=worlds, device=dev, seed=0, auto_reset=1,
-                     world_offset=rank * worlds)
-    env.reset_pose()
-    rng = np.random.default_rng(7 + rank)
-    acts = [torch.from_numpy(random_actions(rng, env.N)).to(dev) for _ in range(16)]
-    slots = max(2, int(300e6 / (env.N * BEAMS * 4)) + 1)
-    ring = torch.empty(slots, env.N, BEAMS, device=dev)
+    err = None
+    try:
+        env = StageWorld(BEAMS, scenario='circle', num_worlds=worlds, device=dev, seed=0, auto_reset=1,
+                         world_offset=rank * worlds)
+        env.reset_pose()
+        rng = np.random.default_rng(7 + rank)
+        acts = [torch.from_numpy(random_actions(rng, env.N)).to(dev) for _ in range(16)]
+        slots = max(2, int(300e6 / (env.N * BEAMS * 4)) + 1)
+        ring = torch.empty(slots, env.N, BEAMS, device=dev)
 
-    def tick(i):
-        env.control_vel(acts[i % 16], obs_out=ring[i % slots])
-    for i in range(10):
-        tick(i)
-    torch.cuda.synchronize(dev)
-    G = 2 * max(1, min(n, 2 * slots) // 2)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        for i in range(G):
+        def tick(i):
+            env.control_vel(acts[i % 16], obs_out=ring[i % slots])
+        for i in range(10):
             tick(i)
-    graph.replay()
-    torch.cuda.synchronize(dev)
-    dist.barrier()
+        torch.cuda.synchronize(dev)
+        G = 2 * max(1, min(n, 2 * slots) // 2)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(G):
+                tick(i)
+        graph.replay()
+        torch.cuda.synchronize(dev)
+    except Exception as e:                               # every rank must still reach the collectives below
+        err = repr(e)
+    ok = torch.tensor([0.0 if err else 1.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if float(ok.item()) == 0.0:
+        return {'error': err or 'set-up failed on another rank'}
     ms = gpu_time(torch, dev, lambda i: graph.replay(), max(1, n // G), warm=1) / G
     t = torch.tensor([ms], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
