@@ -318,6 +318,14 @@ int rlca_policy_backward(rlca_policy *pol, const float *params_dev, const float 
 int rlca_adam_step(float *params_dev, const float *grads_dev, float *exp_avg_dev, float *exp_avg_sq_dev, int64_t n,
                    float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale, void *stream);
 
+/* The same step for the flat parameter buffer of a policy whose workspace is `pol` (all RLCA_POLICY_NTENSORS tensors,
+ * padded layout of rlca_policy_param_offset): one kernel that also writes the derived copies of the fc1 weights the
+ * tensor-core GEMMs read (tf32 hi / lo parts and their transposes), so the next rlca_policy_forward does not spend a
+ * pass on them.  Same arithmetic, bit for bit, as rlca_adam_step followed by rlca_policy_weights_changed. */
+int rlca_policy_adam_step(rlca_policy *pol, float *params_dev, const float *grads_dev, float *exp_avg_dev,
+                          float *exp_avg_sq_dev, float lr, float beta1, float beta2, float eps, int32_t step,
+                          float grad_scale, void *stream);
+
 /* generate_train_data (model/ppo.py:122-139): GAE(gamma, lam) over (T,N) time-major arrays,
  * reverse recurrence evaluated in float64 like the reference's numpy; fp32 outputs. */
 int rlca_gae(const float *rewards_dev, const float *values_dev, const float *last_value_dev, const uint8_t *dones_dev,

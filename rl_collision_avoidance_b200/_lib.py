@@ -90,6 +90,8 @@ SYMBOLS = {
     'rlca_policy_backward': (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P]),
     'rlca_adam_step': (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
                                  C.c_float, _P]),
+    'rlca_policy_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32,
+                                        C.c_float, _P]),
     'rlca_gae': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P, _P, _P]),
     'rlca_adv_moments': (C.c_int, [_P, C.c_int64, _P, _P]),
     'rlca_adv_apply': (C.c_int, [_P, C.c_int64, _P, _P, _P]),

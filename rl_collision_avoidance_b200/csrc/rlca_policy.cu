@@ -110,6 +110,7 @@ struct rlca_policy {
     float *WimgB;    // same for the backward kernel (per tower: conv1 weights | conv2 weights regrouped by tap)
     int conv_bwd_dirty;
     int wc_dirty;        // Wc (the CUDA-core conv kernels' weight block) is rebuilt only when one of them is about to run
+    int w1_split_valid;  // W1s / W1Ts already hold the current fc1 weights (written by rlca_policy_adam_step)
     cudaEvent_t fc_grads_event;   // optional: recorded by rlca_policy_backward once every gradient outside the conv towers is final
     int reserved_sms;             // SMs the persistent conv tower backward leaves free while that event is set (for the collective)
     // ---- side streams of the backward: the work that is not on the chain heads -> dX -> dF -> conv towers (transposed
@@ -901,6 +902,68 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
     p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// The optimizer step of a policy workspace: Adam over the whole flat buffer AND the tf32 hi / lo split of the two fc1
+// weight matrices (97 % of the parameters) with their transposes, which the next forward / backward GEMMs read - the
+// split used to be a pass of its own at the head of every forward after a step (10 us at the critical path's start).
+// Blocks below tile_blocks take a 32 x 32 tile of fc1w[tower] (coalesced rows in, coalesced rows out, the transposed
+// copies through a padded shared tile, as split_both_kernel); the others take the parameters outside those ranges
+// element-wise.  The arithmetic is adam_kernel's, expression for expression.
+struct AdamSplitArgs {
+    float *p, *m, *v;
+    const float *g;
+    long long n, w_off0, w_off1;
+    float *hi0, *lo0, *thi0, *tlo0, *hi1, *lo1, *thi1, *tlo1;
+    float lr, b1, b2, eps, bc1, bc2_sqrt, grad_scale;
+    int tile_blocks;
+};
+
+__device__ __forceinline__ float adam_update_one(const AdamSplitArgs &a, long long i)
+{
+    const float gi = a.g[i] * a.grad_scale;
+    const float mi = fmaf(a.b1, a.m[i], (1.0f - a.b1) * gi);
+    const float vi = fmaf(a.b2, a.v[i], (1.0f - a.b2) * gi * gi);
+    a.m[i] = mi; a.v[i] = vi;
+    const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+    float pv = a.p[i];
+    pv -= (a.lr / a.bc1) * (mi / denom);
+    a.p[i] = pv;
+    return pv;
+}
+
+__global__ void __launch_bounds__(256) adam_split_kernel(const AdamSplitArgs a)
+{
+    __shared__ float tile[32][33];
+    constexpr long long WSZ = 256LL * FEAT;
+    if ((int)blockIdx.x < a.tile_blocks) {
+        const int t = blockIdx.x >> 10, rem = blockIdx.x & 1023;       // 8 x 128 tiles per tower
+        const int r0 = (rem >> 7) * 32, c0 = (rem & 127) * 32;
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+        const long long base = t ? a.w_off1 : a.w_off0;
+        float *hi = t ? a.hi1 : a.hi0, *lo = t ? a.lo1 : a.lo0, *thi = t ? a.thi1 : a.thi0, *tlo = t ? a.tlo1 : a.tlo0;
+        for (int i = ty; i < 32; i += 8) {
+            const long long e = (long long)(r0 + i) * FEAT + c0 + tx;
+            const float x = adam_update_one(a, base + e);
+            const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            hi[e] = h;
+            lo[e] = x - h;
+            tile[i][tx] = x;
+        }
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8) {
+            const float x = tile[tx][i];
+            const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            const long long e = (long long)(c0 + i) * 256 + r0 + tx;
+            thi[e] = h;
+            tlo[e] = x - h;
+        }
+    } else {
+        long long i = (long long)(blockIdx.x - a.tile_blocks) * 256 + threadIdx.x;
+        if (i >= a.w_off0) i += WSZ;               // skip the two fc1w ranges
+        if (i >= a.w_off1) i += WSZ;
+        if (i < a.n) adam_update_one(a, i);
+    }
+}
+
 // GAE as a blocked segmented scan over time (generate_train_data, model/ppo.py:122-139).
 // The recurrence A_t = delta_t + k_t A_{t+1} (k_t = gamma*lam*(1-d_t); a done flag cuts the segment) is affine, so a
 // chunk of GAE_CHUNK steps composes to A_first = P + Q * A_after.  Block = 8 time chunks x 32 agents:
@@ -1206,6 +1269,7 @@ extern "C" int rlca_policy_weights_changed(rlca_policy *p)
     p->weights_dirty = 1;
     p->conv_bwd_dirty = 1;
     p->wc_dirty = 1;
+    p->w1_split_valid = 0;
     return RLCA_OK;
 }
 
@@ -1217,6 +1281,7 @@ extern "C" int rlca_policy_set_tensor_cores(rlca_policy *p, int32_t enable)
     p->weights_dirty = 1;
     p->conv_bwd_dirty = 1;
     p->wc_dirty = 1;
+    p->w1_split_valid = 0;
     return RLCA_OK;
 }
 
@@ -1267,7 +1332,7 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
             float *Wh = pol->W1s + (size_t)(2 * t) * WSZ, *Wl = Wh + WSZ;
             pr[t] = RlcaTcProblem{Fh, Fl, Wh, Wl, FEAT, FEAT, pol->P + (size_t)t * B * 256, nullptr};
         }
-        if (pol->weights_dirty) {          // hi/lo (and transposed) copies of W1 are refreshed only after a weight change
+        if (pol->weights_dirty && !pol->w1_split_valid) {   // hi/lo (and transposed) copies of W1 after a weight change the optimizer step did not make
             const float *w[2] = {ta.fc1w, tc.fc1w};
             float *hi[2], *lo[2], *thi[2], *tlo[2];
             for (int t = 0; t < 2; ++t) {
@@ -1284,7 +1349,7 @@ extern "C" int rlca_policy_forward(rlca_policy *pol, const float *params, const 
         if (rc) return rc;
         rlca_tc_splitk_bias_relu(pol->P, splits, split_stride, (long long)nb * 256, ta.fc1b, tc.fc1b, nb, 256, pol->X,
                                  pol->X + (size_t)nb * XLD, XLD, s);
-        pol->launches += pol->weights_dirty ? 3 : 2;
+        pol->launches += (pol->weights_dirty && !pol->w1_split_valid) ? 3 : 2;
     } else {
         // fc1: X[:, :256] = relu(F W1^T + b1)
         g.M = nb; g.N = 256; g.K = FEAT; g.lda = FEAT; g.ldb = FEAT; g.ldc = XLD; g.relu = 1;
@@ -1509,6 +1574,39 @@ extern "C" int rlca_adam_step(float *params, const float *grads, float *exp_avg,
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr,
                                                                             beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
     RLCA_CUDA_TRY(cudaGetLastError());
+    return RLCA_OK;
+}
+
+extern "C" int rlca_policy_adam_step(rlca_policy *pol, float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                                     float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                                     void *stream)
+{
+    if (!pol || !params || !grads || !exp_avg || !exp_avg_sq || step < 1)
+        return rlca_set_err(RLCA_ERR_INVALID, "bad Adam arguments");
+    const int64_t n = tensor_offset(RLCA_POLICY_NTENSORS);
+    const float bc1 = 1.0f - powf(beta1, (float)step);
+    const float bc2 = 1.0f - powf(beta2, (float)step);
+    if (pol->use_tc) {
+        const size_t WSZ = (size_t)256 * FEAT;
+        AdamSplitArgs a{};
+        a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.n = n;
+        a.w_off0 = tensor_offset(T_CV1W + 4); a.w_off1 = tensor_offset(T_CRT0 + 4);
+        a.hi0 = pol->W1s; a.lo0 = a.hi0 + WSZ; a.hi1 = pol->W1s + 2 * WSZ; a.lo1 = a.hi1 + WSZ;
+        a.thi0 = pol->W1Ts; a.tlo0 = a.thi0 + WSZ; a.thi1 = pol->W1Ts + 2 * WSZ; a.tlo1 = a.thi1 + WSZ;
+        a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.bc1 = bc1; a.bc2_sqrt = sqrtf(bc2); a.grad_scale = grad_scale;
+        a.tile_blocks = 2 * 8 * 128;
+        const int64_t rest = n - 2 * (int64_t)WSZ;
+        adam_split_kernel<<<(unsigned)(a.tile_blocks + (rest + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr,
+                                                                                beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+    }
+    RLCA_CUDA_TRY(cudaGetLastError());
+    pol->weights_dirty = 1;                       // the conv weight images are still rebuilt at the next forward / backward
+    pol->conv_bwd_dirty = 1;
+    pol->wc_dirty = 1;
+    pol->w1_split_valid = pol->use_tc ? 1 : 0;
+    pol->launches += 1;
     return RLCA_OK;
 }
 

@@ -246,10 +246,11 @@ class Adam:
             self.peer.step(self, grad_scale)
             p.weights_changed()
             return
-        _lib.check(p.lib.rlca_adam_step(_ptr(p.flat), _ptr(p.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
-                                        p.flat_size, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count,
-                                        grad_scale, p._stream()))
-        p.weights_changed()
+        # one kernel: Adam over the flat buffer + the tf32 hi / lo split (and transposes) of the fc1 weights that the
+        # tensor-core GEMMs of the next forward / backward read; it marks the workspace's other weight images stale
+        _lib.check(p.lib.rlca_policy_adam_step(p._workspace(1), _ptr(p.flat), _ptr(p.grad), _ptr(self.exp_avg),
+                                               _ptr(self.exp_avg_sq), self.lr, self.betas[0], self.betas[1], self.eps,
+                                               self.step_count, grad_scale, p._stream()))
 
     def state_dict(self):
         if self.peer is not None:           # sharded moments: read the other ranks' shards through the peer mappings
