@@ -77,3 +77,26 @@ def test_reference_checkpoint_fixtures_have_the_23_tensors():
         sd = torch.load(os.path.join(sys_path, 'golden', 'checkpoints', name + '.pth'), map_location='cpu')
         assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s)) for k, s in SHAPES]
         assert all(v.dtype == torch.float32 for v in sd.values())
+
+
+def test_transform_buffer_matches_reference_golden():
+    """model/ppo.py:22-54: the rollout buffer (per step: states of every robot, action, reward, done, logprob, value)
+    stacked into eight (T, N, ...) arrays.  The reference's own function ran on a seeded buffer
+    (tools/make_golden_buffer.py -> tests/golden/buffer_golden.npz); ours takes the per-step BATCHED form of the same
+    data and must return the same eight arrays in the same order."""
+    import os
+    import torch
+    from rl_collision_avoidance_b200.model.ppo import transform_buffer
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'buffer_golden.npz'))
+    T = g['in_obs'].shape[0]
+    buff = []
+    for t in range(T):
+        state = (torch.from_numpy(g['in_obs'][t]), torch.from_numpy(g['in_goal'][t]), torch.from_numpy(g['in_speed'][t]))
+        buff.append((state, torch.from_numpy(g['in_a'][t]), torch.from_numpy(g['in_r'][t]), torch.from_numpy(g['in_d'][t]),
+                     torch.from_numpy(g['in_l'][t]), torch.from_numpy(g['in_v'][t])))
+    got = transform_buffer(buff)
+    assert len(got) == 8
+    for name, arr in zip(('s', 'goal', 'speed', 'a', 'r', 'd', 'l', 'v'), got):
+        ref = g['out_' + name]
+        assert tuple(arr.shape) == ref.shape, name
+        assert np.array_equal(arr.numpy(), ref), name
